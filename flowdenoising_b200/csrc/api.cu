@@ -1,0 +1,509 @@
+// C ABI of libfdn_b200.so (see include/fdn_b200.h) and the host-side pass engine.
+//
+// The pass engine restates, as batched GPU work, the reference's per-slice loops
+// (/root/reference/src/flowdenoising.py:306-327 and the Y/X twins :329-373):
+//   for every output slice s: two chains (backward d = 1..r, then the centre tap, then forward d = 1..r), each
+//   chain seeding the flow of neighbour d+1 with neighbour d's flow, tmp += warp(neigh, flow) * kernel[i].
+// Here all output slices of a chunk advance through the chain together (one launch per stage per chain step),
+// and the per-slice work that depends on one image only (pyramid levels and polynomial expansions) is computed
+// once per slice per pass and cached in HBM instead of once per pair as the reference does.
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <vector>
+
+#include "fdn_internal.cuh"
+
+namespace fdn {
+
+static thread_local char g_err[512] = "";
+int64_t g_launches = 0;
+
+void set_error(const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+// ---- per-kernel event timing ----
+bool g_prof_on = false;
+struct ProfRec {
+    cudaEvent_t a, b;
+    int id;
+    double bytes;
+};
+static std::vector<ProfRec> g_prof;
+static std::vector<cudaEvent_t> g_event_pool;
+static const char* const g_kernel_names[K_COUNT] = {
+    "k_blur_rows", "k_blur_cols", "k_resize_linear_img", "k_polyexp", "k_flow_iter", "k_flow_area_down",
+    "k_flow_upsample", "k_warp_acc", "k_gauss_axis", "k_gauss_rows", "k_transpose"};
+
+static cudaEvent_t get_event()
+{
+    if (!g_event_pool.empty()) {
+        cudaEvent_t e = g_event_pool.back();
+        g_event_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+
+void prof_begin(int id, double bytes, cudaStream_t st)
+{
+    ProfRec r;
+    r.a = get_event();
+    r.b = get_event();
+    r.id = id;
+    r.bytes = bytes;
+    cudaEventRecord(r.a, st);
+    g_prof.push_back(r);
+}
+
+void prof_end(cudaStream_t st) { cudaEventRecord(g_prof.back().b, st); }
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Geometry {
+    int nl;  // extra levels
+    int hs[FDN_MAX_LEVELS + 1], ws[FDN_MAX_LEVELS + 1], ksz[FDN_MAX_LEVELS + 1];
+    double sigma[FDN_MAX_LEVELS + 1];
+    size_t R_off[FDN_MAX_LEVELS + 1];  // float offset of level k inside one slot
+    size_t R_slot;                     // floats per slot
+};
+
+static int make_geometry(int H, int W, int levels, Geometry* g)
+{
+    if (levels > FDN_MAX_LEVELS) levels = FDN_MAX_LEVELS;
+    if (levels < 0) levels = 0;
+    g->nl = fdn_level_geometry(H, W, levels, g->hs, g->ws, g->ksz, g->sigma);
+    size_t off = 0;
+    for (int k = 0; k <= g->nl; k++) {
+        g->R_off[k] = off;
+        off += (size_t)5 * g->hs[k] * g->ws[k];
+    }
+    g->R_slot = off;
+    for (int k = 0; k <= g->nl; k++)
+        if (g->ksz[k] > FDN_MAX_KSZ) {
+            set_error("pyramid level %d needs a %d-tap smoothing kernel (max %d)", k, g->ksz[k], FDN_MAX_KSZ);
+            return FDN_ERR_INVALID;
+        }
+    return FDN_OK;
+}
+
+static int check_of(const fdn_of_params* of)
+{
+    FDN_CHECK_ARG(of->winsize >= 1 && of->winsize <= 33, "winsize %d unsupported (1..33)", of->winsize);
+    FDN_CHECK_ARG(of->iterations >= 1, "iterations must be >= 1");
+    FDN_CHECK_ARG(of->poly_n >= 1 && of->poly_n <= 7, "poly_n %d unsupported (1..7)", of->poly_n);
+    FDN_CHECK_ARG(of->levels >= 0, "levels must be >= 0");
+    return FDN_OK;
+}
+
+// Pyramid + polynomial expansion of `n` images (view-strided input, image b = input slice in_map.slot(b)) into
+// R slots R_map.slot(b). tmpA/tmpB/img: scratch of n*H*W floats each.
+static int build_R(const float* in, int64_t in_ss, int64_t in_rs, SlotMap in_map, int n, int H, int W,
+                   const Geometry& g, const PolyConsts& pc, float* R, SlotMap R_map, float* tmpA, float* tmpB,
+                   float* img, cudaStream_t st)
+{
+    int rc;
+    for (int k = 0; k <= g.nl; k++) {
+        BlurTaps bt;
+        if ((rc = prepare_blur_taps(g.ksz[k], g.sigma[k], &bt))) return rc;
+        const int h = g.hs[k], w = g.ws[k];
+        if ((rc = launch_blur_rows(in, in_ss, in_rs, in_map, tmpA, n, H, W, bt, st))) return rc;
+        const float* level_img;
+        if (h == H && w == W) {
+            if ((rc = launch_blur_cols(tmpA, img, n, H, W, bt, st))) return rc;
+            level_img = img;
+        } else {
+            if ((rc = launch_blur_cols(tmpA, tmpB, n, H, W, bt, st))) return rc;
+            if ((rc = launch_resize_linear_img(tmpB, n, H, W, img, (int64_t)h * w, h, w, st))) return rc;
+            level_img = img;
+        }
+        if ((rc = launch_polyexp(level_img, (int64_t)h * w, R + g.R_off[k], (int64_t)g.R_slot, R_map, n, h, w, pc,
+                                 st)))
+            return rc;
+    }
+    return FDN_OK;
+}
+
+// Farneback for a batch of n pairs whose polynomial expansions are cached in R (pair b: prev = map0.slot(b),
+// next = map1.slot(b)). P: (n, H, W, 2) initial flow in / final flow out. S1, S2: scratch of the same size.
+static int farneback_batch(const float* R, const Geometry& g, SlotMap map0, SlotMap map1, float* P, float* S1,
+                           float* S2, int n, int H, int W, const fdn_of_params& of, cudaStream_t st)
+{
+    int rc;
+    float* cur = nullptr;
+    int ch = 0, cw = 0;
+    for (int k = g.nl; k >= 0; k--) {
+        const int h = g.hs[k], w = g.ws[k];
+        const size_t fbytes = sizeof(float) * 2 * (size_t)n * h * w;
+        if (k == g.nl) {
+            if (of.use_prev_flow) {
+                if (k == 0) {
+                    cur = P;  // same-size INTER_AREA resize times 1
+                } else {
+                    if ((rc = launch_flow_area_down(P, n, H, W, S1, h, w, (float)ldexp(1.0, -k), st))) return rc;
+                    cur = S1;
+                }
+            } else {
+                cur = (k == 0) ? P : S1;
+                FDN_CUDA(cudaMemsetAsync(cur, 0, fbytes, st));
+            }
+        } else {
+            float* other = (cur == S1) ? S2 : S1;
+            if ((rc = launch_flow_upsample(cur, n, ch, cw, other, h, w, st))) return rc;
+            cur = other;
+        }
+        for (int it = 0; it < of.iterations; it++) {
+            const bool last = (k == 0 && it == of.iterations - 1);
+            float* dst = last ? P : ((cur == S1) ? S2 : S1);
+            if (dst == cur) dst = S1;  // single level, single iteration: P -> S1, copied back below
+            if ((rc = launch_flow_iter(R + g.R_off[k], (int64_t)g.R_slot, map0, map1, cur, dst, n, h, w, of.winsize,
+                                       st)))
+                return rc;
+            cur = dst;
+        }
+        ch = h; cw = w;
+    }
+    if (cur != P) FDN_CUDA(cudaMemcpyAsync(P, cur, sizeof(float) * 2 * (size_t)n * H * W, cudaMemcpyDeviceToDevice, st));
+    return FDN_OK;
+}
+
+struct PassPlan {
+    int chunk, r, slots, full_wrap;
+    Geometry g;
+    size_t off_R, off_P, off_S1, off_S2, total;
+};
+
+static int make_plan(const fdn_view& v, int klen, const fdn_of_params& of, int chunk, PassPlan* p)
+{
+    int rc;
+    FDN_CHECK_ARG(klen >= 1 && (klen & 1), "kernel length must be odd (src/flowdenoising.py:309)");
+    FDN_CHECK_ARG(v.n_in >= 1 && v.n_out >= 1 && v.H >= 1 && v.W >= 1, "empty view");
+    p->r = klen / 2;
+    if (v.periodic) {
+        FDN_CHECK_ARG(v.halo == 0 && v.n_in == v.n_out, "periodic views must have halo == 0 and n_in == n_out");
+    } else {
+        FDN_CHECK_ARG(v.halo >= p->r && v.n_in >= v.n_out + v.halo + p->r,
+                      "non-periodic view needs >= r halo slices on both sides (r=%d, halo=%d, n_in=%d, n_out=%d)",
+                      p->r, v.halo, v.n_in, v.n_out);
+    }
+    if ((rc = check_of(&of))) return rc;
+    if ((rc = make_geometry(v.H, v.W, of.levels, &p->g))) return rc;
+    if (chunk <= 0 || chunk > v.n_out) chunk = v.n_out;
+    p->chunk = chunk;
+    p->full_wrap = v.periodic && (chunk + 2 * p->r >= v.n_in);
+    p->slots = p->full_wrap ? v.n_in : chunk + 2 * p->r;
+    const size_t fl = sizeof(float) * 2 * (size_t)chunk * v.H * v.W;
+    size_t off = 0;
+    p->off_R = off;  off += align_up(sizeof(float) * p->g.R_slot * (size_t)p->slots, 256);
+    p->off_P = off;  off += align_up(fl, 256);
+    p->off_S1 = off; off += align_up(fl, 256);
+    p->off_S2 = off; off += align_up(fl, 256);
+    p->total = off;
+    return FDN_OK;
+}
+
+static int filter_axis_of(const float* d_in, float* d_out, const fdn_view& v, const double* kernel, int klen,
+                          const fdn_of_params& of, int chunk, void* ws, size_t ws_bytes, cudaStream_t st)
+{
+    int rc;
+    PassPlan p;
+    if ((rc = make_plan(v, klen, of, chunk, &p))) return rc;
+    if (ws_bytes < p.total || ws == nullptr) {
+        set_error("workspace too small: need %zu bytes, got %zu", p.total, ws_bytes);
+        return FDN_ERR_WORKSPACE;
+    }
+    const int r = p.r, H = v.H, W = v.W;
+    char* base = static_cast<char*>(ws);
+    float* R = reinterpret_cast<float*>(base + p.off_R);
+    float* P = reinterpret_cast<float*>(base + p.off_P);
+    float* S1 = reinterpret_cast<float*>(base + p.off_S1);
+    float* S2 = reinterpret_cast<float*>(base + p.off_S2);
+    PolyConsts pc;
+    prepare_poly_consts(of.poly_n, of.poly_sigma, &pc);
+    const int wrap_in = v.periodic ? v.n_in : 0;
+    bool cache_full = false;
+
+    for (int c0 = 0; c0 < v.n_out; c0 += p.chunk) {
+        const int C = v.n_out - c0 < p.chunk ? v.n_out - c0 : p.chunk;
+        const int ubase = c0 + v.halo - r;  // first (unwrapped) input slice this chunk touches
+        // ---- stages 1+2 for every slice the chunk needs (S1/S2 double as image scratch) ----
+        if (!(p.full_wrap && cache_full)) {
+            const int need = p.full_wrap ? v.n_in : C + 2 * r;
+            float* tmpA = S1;
+            float* tmpB = S1 + (size_t)p.chunk * H * W;
+            float* img = S2;
+            for (int sb = 0; sb < need; sb += p.chunk) {
+                const int nb = need - sb < p.chunk ? need - sb : p.chunk;
+                SlotMap in_map{p.full_wrap ? sb : ubase + sb, wrap_in};
+                SlotMap R_map{sb, 0};
+                if ((rc = build_R(d_in, v.in_slice_stride, v.in_row_stride, in_map, nb, H, W, p.g, pc, R, R_map, tmpA,
+                                  tmpB, img, st)))
+                    return rc;
+            }
+            cache_full = p.full_wrap;
+        }
+        // ---- chains ----
+        SlotMap map0 = p.full_wrap ? SlotMap{c0 + v.halo, v.n_in} : SlotMap{r, 0};
+        float* acc = d_out + (int64_t)c0 * v.out_slice_stride;
+        bool first = true;
+        const size_t fbytes = sizeof(float) * 2 * (size_t)C * H * W;
+        for (int dir = 0; dir < 2; dir++) {
+            if (dir == 1) {  // centre tap between the two chains (src/flowdenoising.py:317)
+                SlotMap cmap{c0 + v.halo, wrap_in};
+                if ((rc = launch_warp_acc(d_in, v.in_slice_stride, v.in_row_stride, cmap, nullptr, kernel[r], acc,
+                                          v.out_slice_stride, v.out_row_stride, C, H, W, first ? 1 : 0, st)))
+                    return rc;
+                first = false;
+            }
+            if (r > 0) FDN_CUDA(cudaMemsetAsync(P, 0, fbytes, st));  // prev_flow = zeros (:310, :318)
+            for (int d = 1; d <= r; d++) {
+                const int off = dir == 0 ? -d : d;
+                const int tap = r + off;  // kernel index i (backward: r-1..0, forward: r+1..2r)
+                SlotMap map1 = p.full_wrap ? SlotMap{c0 + v.halo + off, v.n_in} : SlotMap{r + off, 0};
+                if ((rc = farneback_batch(R, p.g, map0, map1, P, S1, S2, C, H, W, of, st))) return rc;
+                SlotMap nmap{c0 + v.halo + off, wrap_in};
+                if ((rc = launch_warp_acc(d_in, v.in_slice_stride, v.in_row_stride, nmap, P, kernel[tap], acc,
+                                          v.out_slice_stride, v.out_row_stride, C, H, W, first ? 1 : 0, st)))
+                    return rc;
+                first = false;
+            }
+        }
+    }
+    return FDN_OK;
+}
+
+}  // namespace fdn
+
+using namespace fdn;
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+int fdn_version(void) { return 100; }
+const char* fdn_last_error(void) { return g_err; }
+int64_t fdn_launch_count(void) { return g_launches; }
+void fdn_reset_launch_count(void) { g_launches = 0; }
+
+void fdn_profile_enable(int on) { g_prof_on = on != 0; }
+
+void fdn_profile_reset(void)
+{
+    for (auto& r : g_prof) { g_event_pool.push_back(r.a); g_event_pool.push_back(r.b); }
+    g_prof.clear();
+}
+
+int fdn_profile_kernel_count(void) { return K_COUNT; }
+const char* fdn_profile_kernel_name(int id) { return (id >= 0 && id < K_COUNT) ? g_kernel_names[id] : ""; }
+
+int fdn_profile_read(int id, double* total_ms, int64_t* launches, double* algorithmic_bytes)
+{
+    FDN_CHECK_ARG(id >= 0 && id < K_COUNT, "bad kernel id %d", id);
+    double ms = 0, bytes = 0;
+    int64_t n = 0;
+    for (auto& r : g_prof) {
+        if (r.id != id) continue;
+        FDN_CUDA(cudaEventSynchronize(r.b));
+        float t = 0;
+        FDN_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+        ms += t; bytes += r.bytes; n++;
+    }
+    if (total_ms) *total_ms = ms;
+    if (launches) *launches = n;
+    if (algorithmic_bytes) *algorithmic_bytes = bytes;
+    return FDN_OK;
+}
+
+int fdn_gaussian_kernel(double sigma, double* taps, int cap)
+{
+    // scipy.ndimage._filters._gaussian_kernel1d(sigma, 0, radius=int(4*sigma+0.5)), which is what the reference's
+    // delta-response loop (src/flowdenoising.py:34-45) returns after trimming the two exact zeros
+    if (!(sigma > 0)) { set_error("sigma must be > 0"); return 0; }
+    const int r = (int)(4.0 * sigma + 0.5);
+    const int n = 2 * r + 1;
+    if (n > cap || !taps) return -n;
+    const double sigma2 = sigma * sigma;
+    double s = 0.0;
+    for (int j = -r; j <= r; j++) {
+        const double x = (double)j;
+        taps[j + r] = exp(-0.5 / sigma2 * (x * x));
+    }
+    for (int j = 0; j < n; j++) s += taps[j];
+    for (int j = 0; j < n; j++) taps[j] /= s;
+    return n;
+}
+
+int fdn_level_geometry(int H, int W, int levels, int* hs, int* ws, int* ksz, double* sigma)
+{
+    int k;
+    double scale;
+    if (levels > FDN_MAX_LEVELS) levels = FDN_MAX_LEVELS;
+    for (k = 0, scale = 1; k < levels; k++) {
+        scale *= 0.5;
+        if (W * scale < 32 || H * scale < 32) break;
+    }
+    const int nl = k;
+    for (k = 0; k <= nl; k++) {
+        scale = ldexp(1.0, -k);
+        const double sg = (1. / scale - 1) * 0.5;
+        int s = (int)lrint(sg * 5) | 1;
+        if (s < 3) s = 3;
+        if (ksz) ksz[k] = s;
+        if (sigma) sigma[k] = sg;
+        if (ws) ws[k] = (int)lrint(W * scale);
+        if (hs) hs[k] = (int)lrint(H * scale);
+    }
+    return nl;
+}
+
+size_t fdn_workspace_bytes(const fdn_view* view, int klen, const fdn_of_params* of, int chunk)
+{
+    if (!view) { set_error("null view"); return 0; }
+    if (!of) return 0;  // the no-OF path needs no workspace
+    PassPlan p;
+    if (make_plan(*view, klen, *of, chunk, &p)) return 0;
+    return p.total;
+}
+
+int fdn_filter_axis(const float* d_in, float* d_out, const fdn_view* view, const double* kernel, int klen,
+                    const fdn_of_params* of, int chunk, void* d_workspace, size_t workspace_bytes, void* stream)
+{
+    FDN_CHECK_ARG(d_in && d_out && view && kernel, "null argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (!of) return fdn_gauss_axis(d_in, d_out, view, kernel, klen, 1, stream);
+    return filter_axis_of(d_in, d_out, *view, kernel, klen, *of, chunk, d_workspace, workspace_bytes, st);
+}
+
+int fdn_gauss_axis(const float* d_in, float* d_out, const fdn_view* view, const double* kernel, int klen, int exact,
+                   void* stream)
+{
+    FDN_CHECK_ARG(d_in && d_out && view && kernel, "null argument");
+    const fdn_view& v = *view;
+    FDN_CHECK_ARG(klen >= 1 && (klen & 1), "kernel length must be odd");
+    if (v.periodic) FDN_CHECK_ARG(v.halo == 0 && v.n_in == v.n_out, "periodic views must have halo == 0");
+    else FDN_CHECK_ARG(v.halo >= klen / 2 && v.n_in >= v.n_out + v.halo + klen / 2, "halo too small");
+    return launch_gauss_axis(d_in, d_out, v, kernel, klen, exact, static_cast<cudaStream_t>(stream));
+}
+
+int fdn_gauss_rows(const float* d_in, float* d_out, int64_t n_rows, int W, const double* kernel, int klen, int exact,
+                   void* stream)
+{
+    FDN_CHECK_ARG(d_in && d_out && kernel && n_rows >= 1 && W >= 1, "bad argument");
+    return launch_gauss_rows(d_in, d_out, n_rows, W, kernel, klen, exact, static_cast<cudaStream_t>(stream));
+}
+
+int fdn_transpose_yx(const float* d_in, float* d_out, int n, int A, int B, void* stream)
+{
+    FDN_CHECK_ARG(d_in && d_out && n >= 1 && A >= 1 && B >= 1, "bad argument");
+    return launch_transpose(d_in, d_out, n, A, B, static_cast<cudaStream_t>(stream));
+}
+
+int fdn_pyramid_level(const float* d_img, int n, int H, int W, int64_t slice_stride, int64_t row_stride, int ksz,
+                      double sigma, int h, int w, float* d_tmp, float* d_out, void* stream)
+{
+    FDN_CHECK_ARG(d_img && d_tmp && d_out && n >= 1, "bad argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc;
+    BlurTaps bt;
+    if ((rc = prepare_blur_taps(ksz, sigma, &bt))) return rc;
+    float* tmpA = d_tmp;
+    float* tmpB = d_tmp + (size_t)n * H * W;
+    if ((rc = launch_blur_rows(d_img, slice_stride, row_stride, SlotMap{0, 0}, tmpA, n, H, W, bt, st))) return rc;
+    if (h == H && w == W) return launch_blur_cols(tmpA, d_out, n, H, W, bt, st);
+    if ((rc = launch_blur_cols(tmpA, tmpB, n, H, W, bt, st))) return rc;
+    return launch_resize_linear_img(tmpB, n, H, W, d_out, (int64_t)h * w, h, w, st);
+}
+
+int fdn_polyexp(const float* d_img, int n, int h, int w, int poly_n, double poly_sigma, float* d_R, void* stream)
+{
+    FDN_CHECK_ARG(d_img && d_R && n >= 1, "bad argument");
+    FDN_CHECK_ARG(poly_n >= 1 && poly_n <= 7, "poly_n %d unsupported (1..7)", poly_n);
+    PolyConsts pc;
+    prepare_poly_consts(poly_n, poly_sigma, &pc);
+    return launch_polyexp(d_img, (int64_t)h * w, d_R, (int64_t)5 * h * w, SlotMap{0, 0}, n, h, w, pc,
+                          static_cast<cudaStream_t>(stream));
+}
+
+int fdn_flow_iteration(const float* d_R0, const float* d_R1, const float* d_flow_in, float* d_flow_out, int n, int h,
+                       int w, int winsize, void* stream)
+{
+    FDN_CHECK_ARG(d_R0 && d_R1 && d_flow_in && d_flow_out && n >= 1, "bad argument");
+    // R0 and R1 are separate dense batches: address both relative to R0 with a slot stride of one image
+    const int64_t stride = (int64_t)5 * h * w;
+    const ptrdiff_t delta = d_R1 - d_R0;
+    FDN_CHECK_ARG(delta % stride == 0, "R1 - R0 must be a multiple of one image (5*h*w floats)");
+    return launch_flow_iter(d_R0, stride, SlotMap{0, 0}, SlotMap{(int)(delta / stride), 0}, d_flow_in, d_flow_out, n,
+                            h, w, winsize, static_cast<cudaStream_t>(stream));
+}
+
+int fdn_flow_area_down(const float* d_flow, int n, int H, int W, float* d_out, int h, int w, float scale, void* stream)
+{
+    FDN_CHECK_ARG(d_flow && d_out && n >= 1, "bad argument");
+    return launch_flow_area_down(d_flow, n, H, W, d_out, h, w, scale, static_cast<cudaStream_t>(stream));
+}
+
+int fdn_flow_upsample(const float* d_flow, int n, int h_in, int w_in, float* d_out, int h, int w, void* stream)
+{
+    FDN_CHECK_ARG(d_flow && d_out && n >= 1, "bad argument");
+    return launch_flow_upsample(d_flow, n, h_in, w_in, d_out, h, w, static_cast<cudaStream_t>(stream));
+}
+
+size_t fdn_farneback_workspace_bytes(int n, int H, int W, const fdn_of_params* of)
+{
+    if (!of || n < 1) { set_error("bad argument"); return 0; }
+    Geometry g;
+    if (make_geometry(H, W, of->levels, &g)) return 0;
+    const size_t fl = align_up(sizeof(float) * 2 * (size_t)n * H * W, 256);
+    return align_up(sizeof(float) * g.R_slot * 2 * (size_t)n, 256) + 2 * fl;
+}
+
+int fdn_farneback(const float* d_prev, const float* d_next, float* d_flow, int n, int H, int W,
+                  const fdn_of_params* of, void* d_workspace, size_t workspace_bytes, void* stream)
+{
+    FDN_CHECK_ARG(d_prev && d_next && d_flow && of && n >= 1, "bad argument");
+    int rc;
+    if ((rc = check_of(of))) return rc;
+    Geometry g;
+    if ((rc = make_geometry(H, W, of->levels, &g))) return rc;
+    const size_t need = fdn_farneback_workspace_bytes(n, H, W, of);
+    if (!d_workspace || workspace_bytes < need) {
+        set_error("workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
+        return FDN_ERR_WORKSPACE;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t fl = align_up(sizeof(float) * 2 * (size_t)n * H * W, 256);
+    char* base = static_cast<char*>(d_workspace);
+    float* R = reinterpret_cast<float*>(base);
+    float* S1 = reinterpret_cast<float*>(base + align_up(sizeof(float) * g.R_slot * 2 * (size_t)n, 256));
+    float* S2 = reinterpret_cast<float*>(reinterpret_cast<char*>(S1) + fl);
+    PolyConsts pc;
+    prepare_poly_consts(of->poly_n, of->poly_sigma, &pc);
+    // slots [0, n): prev images, [n, 2n): next images. S1/S2 double as image scratch (3*n*H*W floats needed).
+    float* tmpA = S1;
+    float* tmpB = S1 + (size_t)n * H * W;
+    float* img = S2;
+    if ((rc = build_R(d_prev, (int64_t)H * W, W, SlotMap{0, 0}, n, H, W, g, pc, R, SlotMap{0, 0}, tmpA, tmpB, img, st)))
+        return rc;
+    if ((rc = build_R(d_next, (int64_t)H * W, W, SlotMap{0, 0}, n, H, W, g, pc, R, SlotMap{n, 0}, tmpA, tmpB, img, st)))
+        return rc;
+    return farneback_batch(R, g, SlotMap{0, 0}, SlotMap{n, 0}, d_flow, S1, S2, n, H, W, *of, st);
+}
+
+int fdn_warp_accumulate(const float* d_neigh, int64_t neigh_slice_stride, int64_t neigh_row_stride,
+                        const float* d_flow, double weight, float* d_acc, int64_t acc_slice_stride,
+                        int64_t acc_row_stride, int n, int H, int W, void* stream)
+{
+    FDN_CHECK_ARG(d_neigh && d_acc && n >= 1, "bad argument");
+    return launch_warp_acc(d_neigh, neigh_slice_stride, neigh_row_stride, SlotMap{0, 0}, d_flow, weight, d_acc,
+                           acc_slice_stride, acc_row_stride, n, H, W, 0, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

@@ -1,0 +1,119 @@
+// Internal declarations shared by the translation units of libfdn_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "fdn_b200.h"
+
+namespace fdn {
+
+// ---- error plumbing (no exceptions across the C ABI) ----
+void set_error(const char* fmt, ...);
+extern int64_t g_launches;
+
+#define FDN_CHECK_ARG(cond, ...)                 \
+    do {                                         \
+        if (!(cond)) {                           \
+            fdn::set_error(__VA_ARGS__);         \
+            return FDN_ERR_INVALID;              \
+        }                                        \
+    } while (0)
+
+#define FDN_CUDA(call)                                                                          \
+    do {                                                                                        \
+        cudaError_t e_ = (call);                                                                \
+        if (e_ != cudaSuccess) {                                                                \
+            fdn::set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__,                 \
+                           cudaGetErrorString(e_));                                             \
+            return FDN_ERR_CUDA;                                                                \
+        }                                                                                       \
+    } while (0)
+
+// after every kernel launch
+#define FDN_LAUNCHED(name)                                                                      \
+    do {                                                                                        \
+        ++fdn::g_launches;                                                                      \
+        cudaError_t e_ = cudaGetLastError();                                                    \
+        if (e_ != cudaSuccess) {                                                                \
+            fdn::set_error("launch of %s failed at %s:%d: %s", name, __FILE__, __LINE__,        \
+                           cudaGetErrorString(e_));                                             \
+            return FDN_ERR_CUDA;                                                                \
+        }                                                                                       \
+    } while (0)
+
+static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- optional per-kernel timing with CUDA events on the launching stream (bench.py roofline) ----
+enum KernelId {
+    K_BLUR_ROWS = 0, K_BLUR_COLS, K_RESIZE_IMG, K_POLYEXP, K_FLOW_ITER, K_FLOW_AREA, K_FLOW_UP, K_WARP_ACC,
+    K_GAUSS_AXIS, K_GAUSS_ROWS, K_TRANSPOSE, K_COUNT
+};
+extern bool g_prof_on;
+void prof_begin(int id, double algorithmic_bytes, cudaStream_t st);
+void prof_end(cudaStream_t st);
+struct ProfScope {
+    cudaStream_t st;
+    bool on;
+    ProfScope(int id, double bytes, cudaStream_t s) : st(s), on(g_prof_on) { if (on) prof_begin(id, bytes, s); }
+    ~ProfScope() { if (on) prof_end(st); }
+};
+
+// ---- constants passed by value to kernels ----
+struct PolyConsts {
+    int n;
+    float g[8], xg[8], xxg[8];  // taps k = 0..n (n <= 7)
+    double ig11, ig03, ig33, ig55;
+};
+void prepare_poly_consts(int n, double sigma, PolyConsts* pc);
+
+#define FDN_MAX_KSZ 159  // Gaussian pyramid smoothing kernel (levels <= 6 -> 159 taps)
+struct BlurTaps {
+    int ksz;
+    float k[FDN_MAX_KSZ];
+};
+int prepare_blur_taps(int ksz, double sigma, BlurTaps* bt);
+
+// Batch addressing of cached per-slice data: image b of a launch lives in slot
+//   s = base + b            (wrap == 0)
+//   s = (base + b) mod wrap (wrap  > 0)
+struct SlotMap {
+    int base, wrap;
+    __host__ __device__ inline int slot(int b) const
+    {
+        int s = base + b;
+        if (wrap > 0) {
+            s %= wrap;
+            if (s < 0) s += wrap;
+        }
+        return s;
+    }
+};
+
+// ---- launchers (each returns an FDN_* status) ----
+// Stage 1
+int launch_blur_rows(const float* in, int64_t in_ss, int64_t in_rs, SlotMap in_map, float* out, int n, int H,
+                     int W, const BlurTaps& bt, cudaStream_t st);
+int launch_blur_cols(const float* in, float* out, int n, int H, int W, const BlurTaps& bt, cudaStream_t st);
+int launch_resize_linear_img(const float* in, int n, int H, int W, float* out, int64_t out_stride, int h, int w,
+                             cudaStream_t st);
+// Stage 2
+int launch_polyexp(const float* img, int64_t img_stride, float* R, int64_t R_stride, SlotMap R_map, int n, int h,
+                   int w, const PolyConsts& pc, cudaStream_t st);
+// Stage 3
+int launch_flow_iter(const float* R, int64_t R_stride, SlotMap map0, SlotMap map1, const float* flow_in,
+                     float* flow_out, int n, int h, int w, int winsize, cudaStream_t st);
+int launch_flow_area_down(const float* flow, int n, int H, int W, float* out, int h, int w, float scale,
+                          cudaStream_t st);
+int launch_flow_upsample(const float* flow, int n, int hin, int win, float* out, int h, int w, cudaStream_t st);
+// Stage 4
+int launch_warp_acc(const float* neigh, int64_t n_ss, int64_t n_rs, SlotMap n_map, const float* flow, double weight,
+                    float* acc, int64_t a_ss, int64_t a_rs, int n, int H, int W, int first, cudaStream_t st);
+// no-OF
+int launch_gauss_axis(const float* in, float* out, const fdn_view& v, const double* k, int klen, int exact,
+                      cudaStream_t st);
+int launch_gauss_rows(const float* in, float* out, int64_t rows, int W, const double* k, int klen, int exact,
+                      cudaStream_t st);
+int launch_transpose(const float* in, float* out, int n, int A, int B, cudaStream_t st);
+
+}  // namespace fdn

@@ -1,0 +1,306 @@
+// Stage 1 (Gaussian pyramid) and stage 2 (Farneback polynomial expansion) kernels, sm_100a.
+//
+// Reference behaviour: cv2.calcOpticalFlowFarneback internals reached from
+// /root/reference/src/flowdenoising.py:69-79 (OpenCV 4.13 optflowgf.cpp: GaussianBlur + resize per level,
+// FarnebackPolyExp), specified in SURVEY.md App. A.0-A.2. Arithmetic (operation order, which products are
+// fused, float32 vs float64) follows OpenCV so that results are bit-identical to the CPU reference on
+// AVX2 hosts; this file is compiled with -fmad=false and fuses only where fmaf() is written.
+#include <math.h>
+
+#include "fdn_internal.cuh"
+
+namespace fdn {
+
+// ------------------------------------------------------------------------------------------------
+// host-side constant preparation
+// ------------------------------------------------------------------------------------------------
+int prepare_blur_taps(int ksz, double sigma, BlurTaps* bt)
+{
+    if (ksz < 1 || ksz > FDN_MAX_KSZ || (ksz & 1) == 0) {
+        set_error("pyramid smoothing kernel size %d unsupported (odd, <= %d)", ksz, FDN_MAX_KSZ);
+        return FDN_ERR_INVALID;
+    }
+    bt->ksz = ksz;
+    if (sigma <= 0 && ksz == 3) {  // cv::getGaussianKernel small fixed kernel (level 0)
+        bt->k[0] = 0.25f; bt->k[1] = 0.5f; bt->k[2] = 0.25f;
+        return FDN_OK;
+    }
+    double sx = sigma > 0 ? sigma : ((ksz - 1) * 0.5 - 1) * 0.3 + 0.8;
+    double scale2x = -0.5 / (sx * sx);
+    double t[FDN_MAX_KSZ];
+    double sum = 0;
+    for (int i = 0; i < ksz; i++) {
+        double x = i - (ksz - 1) * 0.5;
+        t[i] = exp(scale2x * x * x);
+        sum += t[i];
+    }
+    sum = 1. / sum;
+    for (int i = 0; i < ksz; i++) bt->k[i] = (float)(t[i] * sum);
+    return FDN_OK;
+}
+
+void prepare_poly_consts(int n, double sigma, PolyConsts* pc)
+{
+    // FarnebackPrepareGaussian: float taps, float64 Gram matrix, closed-form inverse of its block structure
+    if (sigma < 1.1920928955078125e-07) sigma = n * 0.3;
+    float g[16], xg[16], xxg[16];
+    double s = 0.;
+    for (int x = -n; x <= n; x++) {
+        g[x + n] = (float)exp(-x * x / (2 * sigma * sigma));
+        s += g[x + n];
+    }
+    s = 1. / s;
+    for (int x = -n; x <= n; x++) {
+        g[x + n] = (float)(g[x + n] * s);
+        xg[x + n] = (float)(x * g[x + n]);
+        xxg[x + n] = (float)(x * x * g[x + n]);
+    }
+    double G00 = 0, G11 = 0, G33 = 0, G55 = 0;
+    for (int y = -n; y <= n; y++)
+        for (int x = -n; x <= n; x++) {
+            float gg = g[y + n] * g[x + n];
+            G00 += gg;
+            G11 += gg * x * x;
+            G33 += gg * x * x * x * x;
+            G55 += gg * x * x * y * y;
+        }
+    double a = G00, b = G11, c = G33, d = G55;
+    double det3 = a * (c * c - d * d) - b * (b * c - b * d) + b * (b * d - b * c);
+    pc->n = n;
+    pc->ig11 = 1. / b;
+    pc->ig55 = 1. / d;
+    pc->ig03 = -(b * c - b * d) / det3;
+    pc->ig33 = (a * c - b * b) / det3;
+    for (int k = 0; k < 8; k++) { pc->g[k] = pc->xg[k] = pc->xxg[k] = 0.f; }
+    for (int k = 0; k <= n; k++) { pc->g[k] = g[n + k]; pc->xg[k] = xg[n + k]; pc->xxg[k] = xxg[n + k]; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// GaussianBlur: row filter then column filter, BORDER_REFLECT_101
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int reflect101(int p, int len)
+{
+    if (len == 1) return 0;
+    while (p < 0 || p >= len) p = p < 0 ? -p : 2 * (len - 1) - p;
+    return p;
+}
+
+// One thread per output pixel; the taps of neighbouring threads overlap in L1.
+__global__ void __launch_bounds__(128)
+k_blur_rows(const float* __restrict__ in, int64_t in_ss, int64_t in_rs, SlotMap in_map, float* __restrict__ out,
+            int H, int W, BlurTaps bt)
+{
+    const int x = blockIdx.x * 128 + threadIdx.x;
+    const int y = blockIdx.y;
+    const int b = blockIdx.z;
+    if (x >= W) return;
+    const float* s = in + (int64_t)in_map.slot(b) * in_ss + (int64_t)y * in_rs;
+    const int ksz = bt.ksz, r = ksz >> 1;
+    float acc;
+    if (ksz == 3) {
+        // SymmRowSmallVec_32f: fma(centre, k1, (l + r) * k0); a last odd column is OpenCV's scalar tail
+        float lr = __fadd_rn(s[reflect101(x - 1, W)], s[reflect101(x + 1, W)]);
+        acc = x < (W & ~1) ? fmaf(s[x], bt.k[1], __fmul_rn(lr, bt.k[0])) : fmaf(lr, bt.k[0], __fmul_rn(s[x], bt.k[1]));
+    } else if (x >= r && x + r < W) {
+        const float* p = s + (x - r);
+        acc = __fmul_rn(p[0], bt.k[0]);
+        if (x < (W & ~3)) {
+            for (int i = 1; i < ksz; i++) acc = fmaf(p[i], bt.k[i], acc);
+        } else {
+            for (int i = 1; i < ksz; i++) acc = __fadd_rn(acc, __fmul_rn(p[i], bt.k[i]));
+        }
+    } else {
+        acc = __fmul_rn(s[reflect101(x - r, W)], bt.k[0]);
+        if (x < (W & ~3)) {
+            for (int i = 1; i < ksz; i++) acc = fmaf(s[reflect101(x - r + i, W)], bt.k[i], acc);
+        } else {
+            for (int i = 1; i < ksz; i++) acc = __fadd_rn(acc, __fmul_rn(s[reflect101(x - r + i, W)], bt.k[i]));
+        }
+    }
+    out[((int64_t)b * H + y) * W + x] = acc;
+}
+
+__global__ void __launch_bounds__(128)
+k_blur_cols(const float* __restrict__ in, float* __restrict__ out, int H, int W, BlurTaps bt)
+{
+    const int x = blockIdx.x * 128 + threadIdx.x;
+    const int y = blockIdx.y;
+    const int b = blockIdx.z;
+    if (x >= W) return;
+    const float* s = in + (int64_t)b * H * W + x;
+    const int ksz = bt.ksz, r = ksz >> 1;
+    float acc = __fmul_rn(s[(int64_t)y * W], bt.k[r]);
+    const bool fused = (ksz == 3) || x < (W & ~7);  // SymmColumnVec_32f covers multiples of 8 lanes
+    for (int i = 1; i <= r; i++) {
+        float a = s[(int64_t)reflect101(y + i, H) * W];
+        float c = s[(int64_t)reflect101(y - i, H) * W];
+        float ac = __fadd_rn(a, c);
+        acc = fused ? fmaf(ac, bt.k[r + i], acc) : __fadd_rn(acc, __fmul_rn(ac, bt.k[r + i]));
+    }
+    out[((int64_t)b * H + y) * W + x] = acc;
+}
+
+int launch_blur_rows(const float* in, int64_t in_ss, int64_t in_rs, SlotMap in_map, float* out, int n, int H,
+                     int W, const BlurTaps& bt, cudaStream_t st)
+{
+    for (int b0 = 0; b0 < n; b0 += 65535) {
+        int nb = n - b0 < 65535 ? n - b0 : 65535;
+        SlotMap m = in_map;
+        m.base += b0;
+        dim3 grid((unsigned)cdiv(W, 128), (unsigned)H, (unsigned)nb);
+        ProfScope ps(K_BLUR_ROWS, 8.0 * nb * H * W, st);
+        k_blur_rows<<<grid, 128, 0, st>>>(in, in_ss, in_rs, m, out + (int64_t)b0 * H * W, H, W, bt);
+        FDN_LAUNCHED("k_blur_rows");
+    }
+    return FDN_OK;
+}
+
+int launch_blur_cols(const float* in, float* out, int n, int H, int W, const BlurTaps& bt, cudaStream_t st)
+{
+    for (int b0 = 0; b0 < n; b0 += 65535) {
+        int nb = n - b0 < 65535 ? n - b0 : 65535;
+        dim3 grid((unsigned)cdiv(W, 128), (unsigned)H, (unsigned)nb);
+        ProfScope ps(K_BLUR_COLS, 8.0 * nb * H * W, st);
+        k_blur_cols<<<grid, 128, 0, st>>>(in + (int64_t)b0 * H * W, out + (int64_t)b0 * H * W, H, W, bt);
+        FDN_LAUNCHED("k_blur_cols");
+    }
+    return FDN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// resize INTER_LINEAR of the (1-channel) pyramid image, Intel-IPP arithmetic (what the x86 cv2 wheel executes):
+// coord = (d + 0.5) * (S / D) - 0.5 in float64, frac = float(coord - floor(coord)), out = fma(b - a, frac, a),
+// horizontal first, then vertical (probe: bit-exact vs cv2.resize).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void linear_coord_ipp(int d, int S, int D, int& s0, float& f)
+{
+    double c = __dsub_rn(__dmul_rn((double)d + 0.5, (double)S / (double)D), 0.5);
+    double fl = floor(c);
+    s0 = (int)fl;
+    f = (float)__dsub_rn(c, fl);
+    if (s0 < 0) { f = 0.f; s0 = 0; }
+    if (s0 >= S - 1) { f = 0.f; s0 = S - 1; }
+}
+
+__global__ void __launch_bounds__(128)
+k_resize_linear_img(const float* __restrict__ in, int H, int W, float* __restrict__ out, int64_t out_stride, int h, int w)
+{
+    const int dx = blockIdx.x * 128 + threadIdx.x;
+    const int dy = blockIdx.y;
+    const int b = blockIdx.z;
+    if (dx >= w) return;
+    int sx0, sy0;
+    float fx, fy;
+    linear_coord_ipp(dx, W, w, sx0, fx);
+    linear_coord_ipp(dy, H, h, sy0, fy);
+    const int sx1 = min(sx0 + 1, W - 1), sy1 = min(sy0 + 1, H - 1);
+    const float* S0 = in + ((int64_t)b * H + sy0) * W;
+    const float* S1 = in + ((int64_t)b * H + sy1) * W;
+    float r0 = fmaf(__fsub_rn(S0[sx1], S0[sx0]), fx, S0[sx0]);
+    float r1 = fmaf(__fsub_rn(S1[sx1], S1[sx0]), fx, S1[sx0]);
+    out[(int64_t)b * out_stride + (int64_t)dy * w + dx] = fmaf(__fsub_rn(r1, r0), fy, r0);
+}
+
+int launch_resize_linear_img(const float* in, int n, int H, int W, float* out, int64_t out_stride, int h, int w,
+                             cudaStream_t st)
+{
+    for (int b0 = 0; b0 < n; b0 += 65535) {
+        int nb = n - b0 < 65535 ? n - b0 : 65535;
+        dim3 grid((unsigned)cdiv(w, 128), (unsigned)h, (unsigned)nb);
+        ProfScope ps(K_RESIZE_IMG, 4.0 * nb * ((double)H * W + (double)h * w), st);
+        k_resize_linear_img<<<grid, 128, 0, st>>>(in + (int64_t)b0 * H * W, H, W, out + (int64_t)b0 * out_stride,
+                                                  out_stride, h, w);
+        FDN_LAUNCHED("k_resize_linear_img");
+    }
+    return FDN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stage 2: FarnebackPolyExp. Tile of PT x PT outputs per block, input tile with a poly_n halo staged in shared
+// memory (replicate border = clamped loads), float32 vertical moments for PT + 2n columns, float64 horizontal
+// pass. Output layout (h, 5, w).
+// ------------------------------------------------------------------------------------------------
+#define PT 32
+#define PN_MAX 7
+
+__global__ void __launch_bounds__(256)
+k_polyexp(const float* __restrict__ img, int64_t img_stride, float* __restrict__ R, int64_t R_stride, SlotMap R_map,
+          int h, int w, PolyConsts pc)
+{
+    __shared__ float s_in[(PT + 2 * PN_MAX) * (PT + 2 * PN_MAX)];
+    __shared__ float s_row[3][PT][PT + 2 * PN_MAX + 1];
+    const int n = pc.n;
+    const int TW = PT + 2 * n;  // staged tile is TW x TW
+    const int x0 = blockIdx.x * PT, y0 = blockIdx.y * PT, b = blockIdx.z;
+    const float* src = img + (int64_t)b * img_stride;
+    for (int i = threadIdx.x; i < TW * TW; i += 256) {
+        int ty = i / TW, tx = i - ty * TW;
+        int gy = min(max(y0 - n + ty, 0), h - 1), gx = min(max(x0 - n + tx, 0), w - 1);
+        s_in[i] = src[(int64_t)gy * w + gx];
+    }
+    __syncthreads();
+    // vertical pass: PT rows x TW columns
+    for (int i = threadIdx.x; i < PT * TW; i += 256) {
+        int ty = i / TW, tx = i - ty * TW;
+        const float* c = s_in + (ty + n) * TW + tx;
+        float t0 = __fmul_rn(c[0], pc.g[0]), t1 = 0.f, t2 = 0.f;
+        for (int k = 1; k <= n; k++) {
+            float a0 = c[-k * TW], a1 = c[k * TW];
+            float p = __fadd_rn(a0, a1);
+            t0 = __fadd_rn(t0, __fmul_rn(pc.g[k], p));
+            t1 = __fadd_rn(t1, __fmul_rn(pc.xg[k], __fsub_rn(a1, a0)));
+            t2 = __fadd_rn(t2, __fmul_rn(pc.xxg[k], p));
+        }
+        s_row[0][ty][tx] = t0; s_row[1][ty][tx] = t1; s_row[2][ty][tx] = t2;
+    }
+    __syncthreads();
+    // horizontal pass (float64 accumulators; products of two floats stay float exactly as in OpenCV's C++)
+    for (int i = threadIdx.x; i < PT * PT; i += 256) {
+        int ty = i / PT, tx = i - ty * PT;
+        int gy = y0 + ty, gx = x0 + tx;
+        if (gy >= h || gx >= w) continue;
+        const float* r0 = &s_row[0][ty][tx + n];
+        const float* r1 = &s_row[1][ty][tx + n];
+        const float* r2 = &s_row[2][ty][tx + n];
+        float g0 = pc.g[0];
+        double b1 = (double)__fmul_rn(r0[0], g0), b2 = 0, b3 = (double)__fmul_rn(r1[0], g0), b4 = 0,
+               b5 = (double)__fmul_rn(r2[0], g0), b6 = 0;
+        for (int k = 1; k <= n; k++) {
+            double tg = (double)__fadd_rn(r0[k], r0[-k]);
+            g0 = pc.g[k];
+            b1 = __dadd_rn(b1, __dmul_rn(tg, (double)g0));
+            b4 = __dadd_rn(b4, __dmul_rn(tg, (double)pc.xxg[k]));
+            b2 = __dadd_rn(b2, (double)__fmul_rn(__fsub_rn(r0[k], r0[-k]), pc.xg[k]));
+            b3 = __dadd_rn(b3, (double)__fmul_rn(__fadd_rn(r1[k], r1[-k]), g0));
+            b6 = __dadd_rn(b6, (double)__fmul_rn(__fsub_rn(r1[k], r1[-k]), pc.xg[k]));
+            b5 = __dadd_rn(b5, (double)__fmul_rn(__fadd_rn(r2[k], r2[-k]), g0));
+        }
+        float* dst = R + (int64_t)R_map.slot(b) * R_stride + (int64_t)gy * 5 * w + gx;
+        dst[0] = (float)__dmul_rn(b3, pc.ig11);
+        dst[(int64_t)w] = (float)__dmul_rn(b2, pc.ig11);
+        dst[(int64_t)2 * w] = (float)__dadd_rn(__dmul_rn(b1, pc.ig03), __dmul_rn(b5, pc.ig33));
+        dst[(int64_t)3 * w] = (float)__dadd_rn(__dmul_rn(b1, pc.ig03), __dmul_rn(b4, pc.ig33));
+        dst[(int64_t)4 * w] = (float)__dmul_rn(b6, pc.ig55);
+    }
+}
+
+int launch_polyexp(const float* img, int64_t img_stride, float* R, int64_t R_stride, SlotMap R_map, int n, int h,
+                   int w, const PolyConsts& pc, cudaStream_t st)
+{
+    if (pc.n < 1 || pc.n > PN_MAX) {
+        set_error("poly_n %d unsupported (1..%d)", pc.n, PN_MAX);
+        return FDN_ERR_INVALID;
+    }
+    for (int b0 = 0; b0 < n; b0 += 65535) {
+        int nb = n - b0 < 65535 ? n - b0 : 65535;
+        SlotMap m = R_map;
+        m.base += b0;
+        dim3 grid((unsigned)cdiv(w, PT), (unsigned)cdiv(h, PT), (unsigned)nb);
+        ProfScope ps(K_POLYEXP, 24.0 * nb * h * w, st);
+        k_polyexp<<<grid, 256, 0, st>>>(img + (int64_t)b0 * img_stride, img_stride, R, R_stride, m, h, w, pc);
+        FDN_LAUNCHED("k_polyexp");
+    }
+    return FDN_OK;
+}
+
+}  // namespace fdn

@@ -1,0 +1,146 @@
+/*
+ * fdn_b200.h -- C ABI of libfdn_b200.so: the B200 (sm_100a) implementation of FlowDenoising's hot path,
+ * the optical-flow-driven separable Gaussian filter (filter_along_Z/Y/X).
+ *
+ * Every entry point is extern "C", takes plain pointers/sizes (device pointers are raw CUdeviceptr-style
+ * addresses; no torch or C++ types cross this boundary), returns an int status (0 = FDN_OK) and never
+ * throws. fdn_last_error() returns a thread-local description of the last failure.
+ * All device work is enqueued on the caller's stream (`stream` is a cudaStream_t passed as void*; NULL =
+ * the legacy default stream) and is asynchronous with respect to the host unless stated otherwise.
+ *
+ * Reference interfaces these replace (file:line in /root/reference):
+ *   fdn_filter_axis      <- GaussianDenoising.filter_along_{Z,Y,X}  src/flowdenoising.py:175-283 (whole pass:
+ *                           _chunk :160-173, no-OF _slice :133-158, OF _slice :306-373)
+ *   fdn_farneback        <- get_flow_with_prev_flow / get_flow_without_prev_flow  :65-114
+ *                           (= cv2.calcOpticalFlowFarneback call sites :69-79, :98-108)
+ *   fdn_warp_accumulate  <- warp_slice :55-63 (= cv2.remap :60-62) fused with `tmp_slice += ... * kernel[i]` :316
+ *   fdn_gaussian_kernel  <- get_gaussian_kernel :34-45
+ *   stage entry points (fdn_pyramid_level, fdn_polyexp, fdn_flow_iteration, ...) expose the four north-star
+ *   stages one by one so that parity tests can address them.
+ *
+ * Data layouts (all float32 unless noted):
+ *   volume view   : element (s, y, x) at base[s*slice_stride + y*row_stride + x]; strides in ELEMENTS; x is
+ *                   always contiguous. Z pass on [Z][Y][X]: slice_stride=Y*X,row_stride=X; Y pass:
+ *                   slice_stride=X,row_stride=Y*X; X pass runs on the [Z][X][Y] transpose (fdn_transpose_yx).
+ *   image         : dense row-major (h, w)
+ *   flow          : dense (h, w, 2), x component first  (same as OpenCV CV_32FC2)
+ *   R (polyexp)   : dense (h, 5, w): row-interleaved channel planes, channel order as OpenCV
+ *                   (R0=d/dy, R1=d/dx, R2=yy, R3=xx, R4=xy)  -- NOT OpenCV's (h, w, 5)
+ */
+#ifndef FDN_B200_H
+#define FDN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FDN_OK 0
+#define FDN_ERR_INVALID 1   /* bad argument */
+#define FDN_ERR_CUDA 2      /* a CUDA runtime call or kernel launch failed */
+#define FDN_ERR_WORKSPACE 3 /* workspace too small */
+
+#define FDN_MAX_LEVELS 16
+
+/* Farneback parameters (reference constants src/flowdenoising.py:47-53; pyr_scale is fixed at 0.5 like :73) */
+typedef struct fdn_of_params {
+    int levels;          /* -l  (OF_LEVELS = 3): EXTRA pyramid levels, cropped while min(W,H)*0.5^k >= 32 */
+    int winsize;         /* -w  (OF_WINDOW_SIZE = 5) */
+    int iterations;      /* OF_ITERS = 3 */
+    int poly_n;          /* OF_POLY_N = 5 (5 or 7 as in OpenCV) */
+    double poly_sigma;   /* OF_POLY_SIGMA = 1.2 */
+    int use_prev_flow;   /* 1: chain flows (get_flow_with_prev_flow), 0: --recompute_flow */
+} fdn_of_params;
+
+/* Geometry of one volume view of a pass. The view holds n_in slices of (H, W). Output slice s (0..n_out-1)
+ * is centred on input slice s+halo; its neighbours are input slices s+halo+d, d in [-r, r]. If periodic != 0
+ * the neighbour index wraps modulo n_in (single-GPU / whole axis resident: halo = 0, n_out = n_in) exactly like
+ * `% self.vol.shape[0]` in src/flowdenoising.py:312; otherwise the caller guarantees halo >= r slices on both
+ * sides (multi-GPU slabs carry the periodic halo explicitly). */
+typedef struct fdn_view {
+    int n_in, n_out, halo, periodic;
+    int H, W;
+    int64_t in_slice_stride, in_row_stride;    /* input view strides (elements) */
+    int64_t out_slice_stride, out_row_stride;  /* output view strides; out index s is the OUTPUT slice number */
+} fdn_view;
+
+/* ---- library / error handling ---- */
+int fdn_version(void);
+const char* fdn_last_error(void);
+/* Number of this library's kernel launches since the last reset (bench.py "gpu_launches"). */
+int64_t fdn_launch_count(void);
+void fdn_reset_launch_count(void);
+
+/* Optional per-kernel timing: when enabled every kernel launch is bracketed by CUDA events on the launching
+ * stream. fdn_profile_read(id) synchronises on them and returns, for kernel `id` (0 <= id <
+ * fdn_profile_kernel_count()), the summed device time, the number of launches and the summed ALGORITHMIC bytes
+ * (what the stage must read + write once) since fdn_profile_reset(). */
+void fdn_profile_enable(int on);
+void fdn_profile_reset(void);
+int fdn_profile_kernel_count(void);
+const char* fdn_profile_kernel_name(int id);
+int fdn_profile_read(int id, double* total_ms, int64_t* launches, double* algorithmic_bytes);
+
+/* ---- host-side helpers ---- */
+/* get_gaussian_kernel (src/flowdenoising.py:34-45): writes 2*int(4*sigma+0.5)+1 float64 taps, returns the
+ * count (or -needed if cap is too small). */
+int fdn_gaussian_kernel(double sigma, double* taps, int cap);
+/* Pyramid geometry (OpenCV level cropping): returns the number of EXTRA levels run (nl) and
+ * fills hs/ws/ksz/sigma[0..nl]. Any output pointer may be NULL. */
+int fdn_level_geometry(int H, int W, int levels, int* hs, int* ws, int* ksz, double* sigma);
+
+/* ---- whole pass (the hot path) ---- */
+/* Bytes of device workspace fdn_filter_axis needs for this view when it processes `chunk` output slices at a
+ * time (chunk <= 0: all n_out at once). */
+size_t fdn_workspace_bytes(const fdn_view* view, int klen, const fdn_of_params* of, int chunk);
+/* One pass along the view's slice axis: out[s] = sum_i kernel[i] * warp(in[s+halo+i-r], flow_i) with the
+ * reference's chain order and per-tap float32 rounding (src/flowdenoising.py:306-327); `of == NULL` selects
+ * the no-OF path (:133-140). d_in and d_out must not overlap. kernel: klen float64 taps on the HOST. */
+int fdn_filter_axis(const float* d_in, float* d_out, const fdn_view* view, const double* kernel, int klen,
+                    const fdn_of_params* of, int chunk, void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* No-OF pass only, selectable arithmetic: exact != 0 reproduces NumPy's per-tap
+ * float32(float64(acc) + float64(v)*k) bit for bit; exact == 0 uses float32 FMA (<= ~2 ulp, HBM-bound). */
+int fdn_gauss_axis(const float* d_in, float* d_out, const fdn_view* view, const double* kernel, int klen,
+                   int exact, void* stream);
+/* Plain separable Gaussian along the contiguous x axis of a dense [n][W] array (X pass without transposes),
+ * periodic wrap. */
+int fdn_gauss_rows(const float* d_in, float* d_out, int64_t n_rows, int W, const double* kernel, int klen,
+                   int exact, void* stream);
+/* Batched 2-D transpose of the last two axes: in [n][A][B] -> out [n][B][A]. */
+int fdn_transpose_yx(const float* d_in, float* d_out, int n, int A, int B, void* stream);
+
+/* ---- stage entry points (parity tests; all operate on a batch of `n` dense images) ---- */
+/* Stage 1: Gaussian pyramid level: GaussianBlur(full-res, ksz, sigma) then bilinear resize to (h, w).
+ * d_tmp: scratch of 2*n*H*W floats. Input images: view-strided (slice_stride/row_stride as in fdn_view). */
+int fdn_pyramid_level(const float* d_img, int n, int H, int W, int64_t slice_stride, int64_t row_stride,
+                      int ksz, double sigma, int h, int w, float* d_tmp, float* d_out, void* stream);
+/* Stage 2: polynomial expansion (h, w) -> R (h, 5, w). */
+int fdn_polyexp(const float* d_img, int n, int h, int w, int poly_n, double poly_sigma, float* d_R, void* stream);
+/* Stage 3: one displacement-update iteration: M = UpdateMatrices(R0, R1, flow_in); flow_out =
+ * BlurSolve(M, winsize). R0/R1: n images each (h, 5, w); flow_in/out: (n, h, w, 2), must not alias. */
+int fdn_flow_iteration(const float* d_R0, const float* d_R1, const float* d_flow_in, float* d_flow_out, int n,
+                       int h, int w, int winsize, void* stream);
+/* Flow resampling between levels: INTER_AREA down-scale * scale (initial flow, coarsest level) and
+ * INTER_LINEAR up-scale * 2 (next finer level). */
+int fdn_flow_area_down(const float* d_flow, int n, int H, int W, float* d_out, int h, int w, float scale,
+                       void* stream);
+int fdn_flow_upsample(const float* d_flow, int n, int h_in, int w_in, float* d_out, int h, int w, void* stream);
+/* Whole Farneback for n independent image pairs (prev = target/centre, next = reference/neighbour; dense
+ * (n, H, W)); flow (n, H, W, 2) is read as the initial flow when use_prev_flow != 0 and overwritten.
+ * Workspace: fdn_farneback_workspace_bytes. (= cv2.calcOpticalFlowFarneback(prev, next, flow, 0.5, ...)) */
+size_t fdn_farneback_workspace_bytes(int n, int H, int W, const fdn_of_params* of);
+int fdn_farneback(const float* d_prev, const float* d_next, float* d_flow, int n, int H, int W,
+                  const fdn_of_params* of, void* d_workspace, size_t workspace_bytes, void* stream);
+/* Stage 4: acc = float32(float64(acc) + float64(remap(neigh, flow)) * weight)  for n images; d_flow == NULL
+ * means identity warp (the centre tap, src/flowdenoising.py:317). neigh/acc are view-strided. */
+int fdn_warp_accumulate(const float* d_neigh, int64_t neigh_slice_stride, int64_t neigh_row_stride,
+                        const float* d_flow, double weight, float* d_acc, int64_t acc_slice_stride,
+                        int64_t acc_row_stride, int n, int H, int W, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FDN_B200_H */

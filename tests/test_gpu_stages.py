@@ -1,0 +1,216 @@
+"""GPU parity tests, stage by stage, through the C ABI (ctypes) against the CPU oracle.
+
+The oracle's C restatement is bit-exact against cv2 4.13 / the reference (tests/test_oracle_golden.py), and the
+kernels follow the same arithmetic, so most comparisons demand bit-exactness; where the GPU legitimately differs
+(float64 summation order of the box window, ~1e-16 relative) the tolerance is written in the test.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import fd_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from flowdenoising_b200.engine import DeviceEngine
+    return DeviceEngine()
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).cuda()
+
+
+def R_to_oracle_layout(R):   # (n, h, 5, w) -> (n, h, w, 5)
+    return np.ascontiguousarray(np.transpose(R, (0, 1, 3, 2)))
+
+
+def R_from_oracle_layout(R):  # (n, h, w, 5) -> (n, h, 5, w)
+    return np.ascontiguousarray(np.transpose(R, (0, 1, 3, 2)))
+
+
+def images(shape, n, seed):
+    return O.synthetic_volume((n,) + shape, seed=seed, noise_sigma=10.0)
+
+
+SHAPES = [(128, 160), (96, 130), (100, 77), (33, 35)]
+
+
+@pytest.mark.parametrize("shape", SHAPES + [(256, 320)])
+def test_pyramid_levels_bit_exact(eng, shape):
+    """Stage 1: GaussianBlur + resize per level == cv2 (via the bit-exact C oracle)."""
+    H, W = shape
+    n = 3
+    imgs = images(shape, n, 1) + np.float32(0.37)     # non-integer values
+    d = dev(imgs)
+    tmp = torch.empty(2 * n * H * W, dtype=torch.float32, device="cuda")
+    for k, (h, w, ksz, sigma) in enumerate(O.level_geometry(H, W, 5)):
+        out = torch.empty((n, h, w), dtype=torch.float32, device="cuda")
+        rc = eng.lib.fdn_pyramid_level(d.data_ptr(), n, H, W, H * W, W, ksz, sigma, h, w, tmp.data_ptr(),
+                                       out.data_ptr(), None)
+        assert rc == 0, eng.lib.fdn_last_error()
+        got = out.cpu().numpy()
+        for i in range(n):
+            ref = O.pyramid_level(imgs[i], ksz, sigma, h, w)
+            assert np.array_equal(got[i], ref), f"level {k} {shape}: max|d|={np.abs(got[i] - ref).max()}"
+
+
+def test_pyramid_strided_view(eng):
+    """Slices taken along Y of a [Z,Y,X] volume (slice_stride = X, row_stride = Y*X) read correctly."""
+    vol = images((40, 48), 36, 2)          # Z=36, Y=40, X=48
+    d = dev(vol)
+    Z, Y, X = vol.shape
+    tmp = torch.empty(2 * Y * Z * X, dtype=torch.float32, device="cuda")
+    out = torch.empty((Y, Z, X), dtype=torch.float32, device="cuda")
+    rc = eng.lib.fdn_pyramid_level(d.data_ptr(), Y, Z, X, X, Y * X, 3, 0.0, Z, X, tmp.data_ptr(), out.data_ptr(), None)
+    assert rc == 0, eng.lib.fdn_last_error()
+    got = out.cpu().numpy()
+    for y in (0, 7, 39):
+        assert np.array_equal(got[y], O.pyramid_level(vol[:, y, :], 3, 0.0, Z, X))
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("poly", [(5, 1.2), (7, 1.5)])
+def test_polyexp_bit_exact(eng, shape, poly):
+    """Stage 2: FarnebackPolyExp."""
+    n = 2
+    imgs = images(shape, n, 3) * np.float32(0.731)
+    h, w = shape
+    R = torch.empty((n, h, 5, w), dtype=torch.float32, device="cuda")
+    rc = eng.lib.fdn_polyexp(dev(imgs).data_ptr(), n, h, w, poly[0], poly[1], R.data_ptr(), None)
+    assert rc == 0, eng.lib.fdn_last_error()
+    got = R_to_oracle_layout(R.cpu().numpy())
+    for i in range(n):
+        ref = O.polyexp(imgs[i], poly[0], poly[1])
+        assert np.array_equal(got[i], ref), f"max|d|={np.abs(got[i] - ref).max()}"
+
+
+@pytest.mark.parametrize("shape", SHAPES + [(40, 300)])
+@pytest.mark.parametrize("win", [5, 9, 15])
+def test_flow_iteration(eng, shape, win):
+    """Stage 3: UpdateMatrices + box blur + solve. The only licence taken vs OpenCV is the float64 summation order
+    of the (2m+1)-wide horizontal window (direct sum vs sliding sum): <= 1e-6 px, >= 99.9 % of values bit-equal."""
+    n = 2
+    h, w = shape
+    imgs = images(shape, 2 * n, 4)
+    R = np.stack([O.polyexp(imgs[i]) for i in range(2 * n)])           # (2n, h, w, 5)
+    rng = np.random.default_rng(5)
+    flow = (rng.standard_normal((n, h, w, 2)) * 1.5).astype(np.float32)
+    flow[0, :4, :4] = 50.0      # out-of-image lookups take the border branch
+    dR = dev(R_from_oracle_layout(R))
+    dflow = dev(flow)
+    out = torch.empty_like(dflow)
+    rc = eng.lib.fdn_flow_iteration(dR[:n].data_ptr(), dR[n:].data_ptr(), dflow.data_ptr(), out.data_ptr(), n, h, w,
+                                    win, None)
+    assert rc == 0, eng.lib.fdn_last_error()
+    got = out.cpu().numpy()
+    for i in range(n):
+        M = O.update_matrices(R[i], R[n + i], flow[i])
+        ref = O.blur_solve(M, win)
+        d = np.abs(got[i] - ref)
+        assert d.max() <= 1e-6, f"max|d|={d.max()}"
+        assert np.mean(got[i] == ref) >= 0.999, f"bit-equal fraction {np.mean(got[i] == ref)}"
+
+
+def test_flow_resampling_bit_exact(eng):
+    rng = np.random.default_rng(6)
+    n = 2
+    for (H, W, h, w) in [(128, 160, 32, 40), (128, 160, 64, 80), (96, 130, 48, 65), (100, 77, 50, 38), (260, 300, 32, 38)]:
+        flow = (rng.standard_normal((n, H, W, 2)) * 2).astype(np.float32)
+        out = torch.empty((n, h, w, 2), dtype=torch.float32, device="cuda")
+        scale = 0.25
+        rc = eng.lib.fdn_flow_area_down(dev(flow).data_ptr(), n, H, W, out.data_ptr(), h, w, scale, None)
+        assert rc == 0, eng.lib.fdn_last_error()
+        for i in range(n):
+            ref = O.resize_area(flow[i], h, w) * np.float32(scale)
+            assert np.array_equal(out[i].cpu().numpy(), ref), (H, W, h, w)
+    for (hin, win, h, w) in [(32, 40, 64, 80), (48, 65, 96, 130), (50, 38, 100, 77), (16, 19, 33, 37)]:
+        flow = (rng.standard_normal((n, hin, win, 2)) * 2).astype(np.float32)
+        out = torch.empty((n, h, w, 2), dtype=torch.float32, device="cuda")
+        rc = eng.lib.fdn_flow_upsample(dev(flow).data_ptr(), n, hin, win, out.data_ptr(), h, w, None)
+        assert rc == 0, eng.lib.fdn_last_error()
+        for i in range(n):
+            ref = O.resize_linear(flow[i], h, w, ipp=False) * np.float32(2)
+            assert np.array_equal(out[i].cpu().numpy(), ref), (hin, win, h, w)
+
+
+def test_warp_accumulate_bit_exact(eng):
+    """Stage 4: cv2.remap (1/32-px quantiser, replicate border) + float64 accumulate rounded per tap."""
+    rng = np.random.default_rng(7)
+    n, H, W = 3, 70, 90
+    imgs = images((H, W), n, 8) + np.float32(0.25)
+    flow = (rng.standard_normal((n, H, W, 2)) * 3).astype(np.float32)
+    flow[1] *= 30   # far out-of-image samples
+    flow[2, ::2] = np.float32(0.015625)   # exact ties of the 1/32 quantiser
+    acc0 = rng.standard_normal((n, H, W)).astype(np.float32) * 10
+    from flowdenoising_b200.engine import DeviceEngine  # noqa: F401
+    acc = dev(acc0)
+    k = 0.19947114020071635
+    eng.warp_accumulate(dev(imgs), dev(flow), k, acc)
+    got = acc.cpu().numpy()
+    for i in range(n):
+        ref = acc0[i].copy()
+        O.lib().fdo_accumulate(ref.ctypes.data_as(C.POINTER(C.c_float)),
+                               O.warp_slice_c(imgs[i], flow[i]).ctypes.data_as(C.POINTER(C.c_float)),
+                               C.c_double(k), C.c_size_t(ref.size))
+        assert np.array_equal(got[i], ref)
+    # identity warp = centre tap
+    acc = dev(acc0)
+    eng.warp_accumulate(dev(imgs), None, k, acc)
+    ref = (acc0.astype(np.float64) + imgs.astype(np.float64) * k).astype(np.float32)
+    assert np.array_equal(acc.cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("case", ["a", "b", "d"])
+def test_farneback_vs_reference_golden(eng, golden, case):
+    """Whole Farneback vs the reference's get_flow outputs (cv2.calcOpticalFlowFarneback): north-star tolerance is
+    mean EPE <= 0.05 px; this implementation is expected to be bit-exact up to isolated last-ulp differences."""
+    from flowdenoising_b200.engine import FlowParams
+    g = golden("flows.npz")
+    v = g[f"{case}_vol"].astype(np.float32)
+    l, w = (int(x) for x in g[f"{case}_lw"])
+    centre = dev(v[0:1])
+    flow = torch.zeros((1,) + v[0].shape + (2,), dtype=torch.float32, device="cuda")
+    p = FlowParams(l, w, 3, 5, 1.2, True)
+    for j in (1, 2, 3):
+        eng.farneback(centre, dev(v[j:j + 1]), flow, p)
+        if j != 2:
+            ref = g[f"{case}_flow_chain{j}"]
+            got = flow[0].cpu().numpy()
+            epe = np.sqrt(((got - ref) ** 2).sum(-1))
+            print(f"case {case} chain{j}: EPE mean {epe.mean():.3e} max {epe.max():.3e} exact {np.mean(got == ref):.5f}")
+            assert epe.mean() <= 1e-6 and epe.max() <= 1e-3
+            assert np.mean(got == ref) >= 0.995
+    f2 = torch.zeros_like(flow)
+    eng.farneback(centre, dev(v[2:3]), f2, FlowParams(l, w, 3, 5, 1.2, False))
+    ref = g[f"{case}_flow_noprev2"]
+    epe = np.sqrt(((f2[0].cpu().numpy() - ref) ** 2).sum(-1))
+    assert epe.mean() <= 1e-6 and epe.max() <= 1e-3
+
+
+def test_farneback_vs_live_cv2(eng):
+    cv2 = pytest.importorskip("cv2")
+    from flowdenoising_b200.engine import FlowParams
+    for shape, l, w, it in [((256, 256), 3, 5, 3), ((64, 256), 3, 5, 3), ((200, 333), 3, 7, 2), ((512, 384), 5, 9, 3),
+                            ((40, 50), 3, 5, 1)]:
+        v = images(shape, 2, 9)
+        ref = cv2.calcOpticalFlowFarneback(v[0], v[1], None, 0.5, l, w, it, 5, 1.2, 0)
+        flow = torch.zeros((1,) + shape + (2,), dtype=torch.float32, device="cuda")
+        eng.farneback(dev(v[0:1]), dev(v[1:2]), flow, FlowParams(l, w, it, 5, 1.2, False))
+        got = flow[0].cpu().numpy()
+        epe = np.sqrt(((got - ref) ** 2).sum(-1))
+        print(f"{shape} l{l} w{w}: EPE mean {epe.mean():.3e} max {epe.max():.3e} exact {np.mean(got == ref):.5f}")
+        assert epe.mean() <= 0.05          # north-star bound
+        assert epe.mean() <= 1e-5 and epe.max() <= 1e-2   # what this implementation actually delivers
+
+
+def test_transpose(eng):
+    rng = np.random.default_rng(10)
+    a = rng.standard_normal((5, 37, 70)).astype(np.float32)
+    out = eng.transpose_yx(dev(a))
+    assert np.array_equal(out.cpu().numpy(), np.transpose(a, (0, 2, 1)))
