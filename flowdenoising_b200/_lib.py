@@ -52,11 +52,17 @@ SIGNATURES = {
     "fdn_gauss_rows": (C.c_int, [c_f32p, c_f32p, c_i64, C.c_int, C.POINTER(C.c_double), C.c_int, C.c_int,
                                  C.c_void_p]),
     "fdn_transpose_yx": (C.c_int, [c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "fdn_transpose_strided": (C.c_int, [c_f32p, c_i64, c_i64, c_f32p, c_i64, c_i64, C.c_int, C.c_int, C.c_int,
+                                        C.c_void_p]),
+    "fdn_copy3d": (C.c_int, [c_f32p, c_i64, c_i64, C.c_int, C.c_int, C.c_int, C.c_int, c_f32p, c_i64, c_i64, C.c_int,
+                             C.c_int, C.c_int, C.c_void_p]),
     "fdn_pyramid_level": (C.c_int, [c_f32p, C.c_int, C.c_int, C.c_int, c_i64, c_i64, C.c_int, C.c_double, C.c_int,
                                     C.c_int, c_f32p, c_f32p, C.c_void_p]),
     "fdn_polyexp": (C.c_int, [c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, c_f32p, C.c_void_p]),
+    "fdn_polyexp_floats": (C.c_size_t, [C.c_int, C.c_int]),
+    "fdn_flow_iteration_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "fdn_flow_iteration": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_int,
-                                     C.c_void_p]),
+                                     C.c_void_p, C.c_size_t, C.c_void_p]),
     "fdn_flow_area_down": (C.c_int, [c_f32p, C.c_int, C.c_int, C.c_int, c_f32p, C.c_int, C.c_int, C.c_float,
                                      C.c_void_p]),
     "fdn_flow_upsample": (C.c_int, [c_f32p, C.c_int, C.c_int, C.c_int, c_f32p, C.c_int, C.c_int, C.c_void_p]),

@@ -39,7 +39,7 @@ static std::vector<ProfRec> g_prof;
 static std::vector<cudaEvent_t> g_event_pool;
 static const char* const g_kernel_names[K_COUNT] = {
     "k_blur_rows", "k_blur_cols", "k_resize_linear_img", "k_polyexp", "k_flow_iter", "k_flow_area_down",
-    "k_flow_upsample", "k_warp_acc", "k_gauss_axis", "k_gauss_rows", "k_transpose"};
+    "k_flow_upsample", "k_warp_acc", "k_gauss_axis", "k_gauss_rows", "k_transpose", "k_copy3d"};
 
 static cudaEvent_t get_event()
 {
@@ -84,7 +84,7 @@ static int make_geometry(int H, int W, int levels, Geometry* g)
     size_t off = 0;
     for (int k = 0; k <= g->nl; k++) {
         g->R_off[k] = off;
-        off += (size_t)5 * g->hs[k] * g->ws[k];
+        off += R_image_floats(g->hs[k], g->ws[k]);
     }
     g->R_slot = off;
     for (int k = 0; k <= g->nl; k++)
@@ -135,7 +135,8 @@ static int build_R(const float* in, int64_t in_ss, int64_t in_rs, SlotMap in_map
 // Farneback for a batch of n pairs whose polynomial expansions are cached in R (pair b: prev = map0.slot(b),
 // next = map1.slot(b)). P: (n, H, W, 2) initial flow in / final flow out. S1, S2: scratch of the same size.
 static int farneback_batch(const float* R, const Geometry& g, SlotMap map0, SlotMap map1, float* P, float* S1,
-                           float* S2, int n, int H, int W, const fdn_of_params& of, cudaStream_t st)
+                           float* S2, int n, int H, int W, const fdn_of_params& of, void* scratch, size_t scratch_bytes,
+                           cudaStream_t st)
 {
     int rc;
     float* cur = nullptr;
@@ -165,7 +166,7 @@ static int farneback_batch(const float* R, const Geometry& g, SlotMap map0, Slot
             float* dst = last ? P : ((cur == S1) ? S2 : S1);
             if (dst == cur) dst = S1;  // single level, single iteration: P -> S1, copied back below
             if ((rc = launch_flow_iter(R + g.R_off[k], (int64_t)g.R_slot, map0, map1, cur, dst, n, h, w, of.winsize,
-                                       st)))
+                                       scratch, scratch_bytes, st)))
                 return rc;
             cur = dst;
         }
@@ -178,7 +179,7 @@ static int farneback_batch(const float* R, const Geometry& g, SlotMap map0, Slot
 struct PassPlan {
     int chunk, r, slots, full_wrap;
     Geometry g;
-    size_t off_R, off_P, off_S1, off_S2, total;
+    size_t off_R, off_P, off_S1, off_S2, off_scratch, scratch_bytes, total;
 };
 
 static int make_plan(const fdn_view& v, int klen, const fdn_of_params& of, int chunk, PassPlan* p)
@@ -206,6 +207,8 @@ static int make_plan(const fdn_view& v, int klen, const fdn_of_params& of, int c
     p->off_P = off;  off += align_up(fl, 256);
     p->off_S1 = off; off += align_up(fl, 256);
     p->off_S2 = off; off += align_up(fl, 256);
+    p->scratch_bytes = flow_iter_scratch_bytes(chunk, v.H, v.W);  // level 0 is the largest
+    p->off_scratch = off; off += align_up(p->scratch_bytes, 256);
     p->total = off;
     return FDN_OK;
 }
@@ -226,6 +229,8 @@ static int filter_axis_of(const float* d_in, float* d_out, const fdn_view& v, co
     float* P = reinterpret_cast<float*>(base + p.off_P);
     float* S1 = reinterpret_cast<float*>(base + p.off_S1);
     float* S2 = reinterpret_cast<float*>(base + p.off_S2);
+    void* scratch = base + p.off_scratch;
+    if ((rc = flow_iter_scratch_init(scratch, p.scratch_bytes, st))) return rc;
     PolyConsts pc;
     prepare_poly_consts(of.poly_n, of.poly_sigma, &pc);
     const int wrap_in = v.periodic ? v.n_in : 0;
@@ -268,7 +273,8 @@ static int filter_axis_of(const float* d_in, float* d_out, const fdn_view& v, co
                 const int off = dir == 0 ? -d : d;
                 const int tap = r + off;  // kernel index i (backward: r-1..0, forward: r+1..2r)
                 SlotMap map1 = p.full_wrap ? SlotMap{c0 + v.halo + off, v.n_in} : SlotMap{r + off, 0};
-                if ((rc = farneback_batch(R, p.g, map0, map1, P, S1, S2, C, H, W, of, st))) return rc;
+                if ((rc = farneback_batch(R, p.g, map0, map1, P, S1, S2, C, H, W, of, scratch, p.scratch_bytes, st)))
+                    return rc;
                 SlotMap nmap{c0 + v.halo + off, wrap_in};
                 if ((rc = launch_warp_acc(d_in, v.in_slice_stride, v.in_row_stride, nmap, P, kernel[tap], acc,
                                           v.out_slice_stride, v.out_row_stride, C, H, W, first ? 1 : 0, st)))
@@ -405,6 +411,22 @@ int fdn_transpose_yx(const float* d_in, float* d_out, int n, int A, int B, void*
     return launch_transpose(d_in, d_out, n, A, B, static_cast<cudaStream_t>(stream));
 }
 
+int fdn_transpose_strided(const float* d_in, int64_t in_sn, int64_t in_sa, float* d_out, int64_t out_sn, int64_t out_sb,
+                          int n, int A, int B, void* stream)
+{
+    FDN_CHECK_ARG(d_in && d_out && n >= 1 && A >= 1 && B >= 1, "bad argument");
+    return launch_transpose_strided(d_in, in_sn, in_sa, d_out, out_sn, out_sb, n, A, B,
+                                    static_cast<cudaStream_t>(stream));
+}
+
+int fdn_copy3d(const float* d_in, int64_t in_sa, int64_t in_sb, int b0, int b_wrap, int c0, int c_wrap, float* d_out,
+               int64_t out_sa, int64_t out_sb, int A, int B, int C, void* stream)
+{
+    FDN_CHECK_ARG(d_in && d_out && A >= 1 && B >= 1 && C >= 1, "bad argument");
+    return launch_copy3d(d_in, in_sa, in_sb, b0, b_wrap, c0, c_wrap, d_out, out_sa, out_sb, A, B, C,
+                         static_cast<cudaStream_t>(stream));
+}
+
 int fdn_pyramid_level(const float* d_img, int n, int H, int W, int64_t slice_stride, int64_t row_stride, int ksz,
                       double sigma, int h, int w, float* d_tmp, float* d_out, void* stream)
 {
@@ -427,20 +449,26 @@ int fdn_polyexp(const float* d_img, int n, int h, int w, int poly_n, double poly
     FDN_CHECK_ARG(poly_n >= 1 && poly_n <= 7, "poly_n %d unsupported (1..7)", poly_n);
     PolyConsts pc;
     prepare_poly_consts(poly_n, poly_sigma, &pc);
-    return launch_polyexp(d_img, (int64_t)h * w, d_R, (int64_t)5 * h * w, SlotMap{0, 0}, n, h, w, pc,
+    return launch_polyexp(d_img, (int64_t)h * w, d_R, (int64_t)R_image_floats(h, w), SlotMap{0, 0}, n, h, w, pc,
                           static_cast<cudaStream_t>(stream));
 }
 
+size_t fdn_polyexp_floats(int h, int w) { return R_image_floats(h, w); }
+
+size_t fdn_flow_iteration_scratch_bytes(int n, int h, int w) { return flow_iter_scratch_bytes(n, h, w); }
+
 int fdn_flow_iteration(const float* d_R0, const float* d_R1, const float* d_flow_in, float* d_flow_out, int n, int h,
-                       int w, int winsize, void* stream)
+                       int w, int winsize, void* d_scratch, size_t scratch_bytes, void* stream)
 {
     FDN_CHECK_ARG(d_R0 && d_R1 && d_flow_in && d_flow_out && n >= 1, "bad argument");
     // R0 and R1 are separate dense batches: address both relative to R0 with a slot stride of one image
-    const int64_t stride = (int64_t)5 * h * w;
+    const int64_t stride = (int64_t)R_image_floats(h, w);
+    int rc;
+    if ((rc = flow_iter_scratch_init(d_scratch, scratch_bytes, static_cast<cudaStream_t>(stream)))) return rc;
     const ptrdiff_t delta = d_R1 - d_R0;
-    FDN_CHECK_ARG(delta % stride == 0, "R1 - R0 must be a multiple of one image (5*h*w floats)");
+    FDN_CHECK_ARG(delta % stride == 0, "R1 - R0 must be a multiple of one image (fdn_polyexp_floats(h, w))");
     return launch_flow_iter(d_R0, stride, SlotMap{0, 0}, SlotMap{(int)(delta / stride), 0}, d_flow_in, d_flow_out, n,
-                            h, w, winsize, static_cast<cudaStream_t>(stream));
+                            h, w, winsize, d_scratch, scratch_bytes, static_cast<cudaStream_t>(stream));
 }
 
 int fdn_flow_area_down(const float* d_flow, int n, int H, int W, float* d_out, int h, int w, float scale, void* stream)
@@ -461,7 +489,7 @@ size_t fdn_farneback_workspace_bytes(int n, int H, int W, const fdn_of_params* o
     Geometry g;
     if (make_geometry(H, W, of->levels, &g)) return 0;
     const size_t fl = align_up(sizeof(float) * 2 * (size_t)n * H * W, 256);
-    return align_up(sizeof(float) * g.R_slot * 2 * (size_t)n, 256) + 2 * fl;
+    return align_up(sizeof(float) * g.R_slot * 2 * (size_t)n, 256) + 2 * fl + align_up(flow_iter_scratch_bytes(n, H, W), 256);
 }
 
 int fdn_farneback(const float* d_prev, const float* d_next, float* d_flow, int n, int H, int W,
@@ -483,6 +511,9 @@ int fdn_farneback(const float* d_prev, const float* d_next, float* d_flow, int n
     float* R = reinterpret_cast<float*>(base);
     float* S1 = reinterpret_cast<float*>(base + align_up(sizeof(float) * g.R_slot * 2 * (size_t)n, 256));
     float* S2 = reinterpret_cast<float*>(reinterpret_cast<char*>(S1) + fl);
+    void* scratch = reinterpret_cast<char*>(S2) + fl;
+    const size_t scratch_bytes = flow_iter_scratch_bytes(n, H, W);
+    if ((rc = flow_iter_scratch_init(scratch, scratch_bytes, st))) return rc;
     PolyConsts pc;
     prepare_poly_consts(of->poly_n, of->poly_sigma, &pc);
     // slots [0, n): prev images, [n, 2n): next images. S1/S2 double as image scratch (3*n*H*W floats needed).
@@ -493,7 +524,7 @@ int fdn_farneback(const float* d_prev, const float* d_next, float* d_flow, int n
         return rc;
     if ((rc = build_R(d_next, (int64_t)H * W, W, SlotMap{0, 0}, n, H, W, g, pc, R, SlotMap{n, 0}, tmpA, tmpB, img, st)))
         return rc;
-    return farneback_batch(R, g, SlotMap{0, 0}, SlotMap{n, 0}, d_flow, S1, S2, n, H, W, *of, st);
+    return farneback_batch(R, g, SlotMap{0, 0}, SlotMap{n, 0}, d_flow, S1, S2, n, H, W, *of, scratch, scratch_bytes, st);
 }
 
 int fdn_warp_accumulate(const float* d_neigh, int64_t neigh_slice_stride, int64_t neigh_row_stride,

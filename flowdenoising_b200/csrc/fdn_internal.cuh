@@ -47,7 +47,7 @@ static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 // ---- optional per-kernel timing with CUDA events on the launching stream (bench.py roofline) ----
 enum KernelId {
     K_BLUR_ROWS = 0, K_BLUR_COLS, K_RESIZE_IMG, K_POLYEXP, K_FLOW_ITER, K_FLOW_AREA, K_FLOW_UP, K_WARP_ACC,
-    K_GAUSS_AXIS, K_GAUSS_ROWS, K_TRANSPOSE, K_COUNT
+    K_GAUSS_AXIS, K_GAUSS_ROWS, K_TRANSPOSE, K_COPY3D, K_COUNT
 };
 extern bool g_prof_on;
 void prof_begin(int id, double algorithmic_bytes, cudaStream_t st);
@@ -101,8 +101,13 @@ int launch_resize_linear_img(const float* in, int n, int H, int W, float* out, i
 int launch_polyexp(const float* img, int64_t img_stride, float* R, int64_t R_stride, SlotMap R_map, int n, int h,
                    int w, const PolyConsts& pc, cudaStream_t st);
 // Stage 3
+// floats one polynomial-expansion image occupies: [h*w] float4 (channels 0-3) + [h*w] float (channel 4), padded to 16 B
+static inline size_t R_image_floats(int h, int w) { size_t p = (size_t)h * w; return 4 * p + ((p + 3) / 4) * 4; }
+size_t flow_iter_scratch_bytes(int n, int h, int w);
+int flow_iter_scratch_init(void* scratch, size_t bytes, cudaStream_t st);
 int launch_flow_iter(const float* R, int64_t R_stride, SlotMap map0, SlotMap map1, const float* flow_in,
-                     float* flow_out, int n, int h, int w, int winsize, cudaStream_t st);
+                     float* flow_out, int n, int h, int w, int winsize, void* scratch, size_t scratch_bytes,
+                     cudaStream_t st);
 int launch_flow_area_down(const float* flow, int n, int H, int W, float* out, int h, int w, float scale,
                           cudaStream_t st);
 int launch_flow_upsample(const float* flow, int n, int hin, int win, float* out, int h, int w, cudaStream_t st);
@@ -115,5 +120,9 @@ int launch_gauss_axis(const float* in, float* out, const fdn_view& v, const doub
 int launch_gauss_rows(const float* in, float* out, int64_t rows, int W, const double* k, int klen, int exact,
                       cudaStream_t st);
 int launch_transpose(const float* in, float* out, int n, int A, int B, cudaStream_t st);
+int launch_transpose_strided(const float* in, int64_t in_sn, int64_t in_sa, float* out, int64_t out_sn, int64_t out_sb,
+                             int n, int A, int B, cudaStream_t st);
+int launch_copy3d(const float* in, int64_t in_sa, int64_t in_sb, int b0, int bw, int c0, int cw, float* out,
+                  int64_t out_sa, int64_t out_sb, int A, int B, int C, cudaStream_t st);
 
 }  // namespace fdn

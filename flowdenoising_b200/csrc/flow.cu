@@ -4,15 +4,21 @@
 // Reference behaviour: the inner loop of cv2.calcOpticalFlowFarneback as called from
 // /root/reference/src/flowdenoising.py:69-79.
 //
-// k_flow_iter design (one launch = one Farneback iteration of one level for a batch of image pairs):
-//   * a block owns a strip of CW columns of one image pair and MARCHES down the rows, exactly like OpenCV's
-//     sliding vertical sum: vsum(y) = vsum(y-1) + float32(M[y+m] - M[y-m-1]) in float64. The float32
-//     subtraction makes OpenCV's box sums history dependent, so a tiled box filter cannot reproduce them
-//     bit for bit; the march does, and it needs no vertical halo (every R0/flow row is read once).
-//   * the five M channels of a pixel are never written to HBM: each thread computes M for its own column from
-//     R0, flow and a bilinear gather of R1, keeps the last 2m+2 rows in a shared-memory ring, updates its
-//     float64 column sums, publishes them to shared memory, and the strip's core threads sum 2m+1 neighbours
-//     (replicate border = clamped column) and solve.
+// k_flow_iter design (one launch = one Farneback iteration of one level for a batch of image pairs).
+// OpenCV's box filter is two RUNNING sums, and both are history dependent in the last bits:
+//   vertical   vsum(y)   = vsum(y-1) + float32(M[y+m] - M[y-m-1])          (float64 accumulator, float32 difference)
+//   horizontal g(x)      = g(x-1)    + (vsum[x+m] - vsum[x-m-1])           (float64, rounding errors persist along x)
+// so a tiled box filter cannot reproduce the reference bit for bit. This kernel reproduces both scans exactly:
+//   * a block owns a strip of CW columns of one image pair and MARCHES down the rows in tiles of TR rows;
+//   * phase V (thread per column, incl. an (m+1 | m)-column halo): M for the new row from R0, flow and a bilinear
+//     gather of R1 (M never touches HBM), ring of the last 2m+2 rows in shared memory, float64 column sums updated
+//     exactly like OpenCV, published to a shared-memory tile;
+//   * phase H (thread per (row, channel) of the tile): the horizontal running sum walks the strip's columns
+//     sequentially, starting from the carry of the strip to the left (same row). Carries travel between the
+//     strips' blocks through global memory with release/acquire flags (blocks of one image are dispatched left
+//     to right, a strip only ever waits on its left neighbour: the decoupled look-back argument);
+//   * phase S (thread per column): regularised 2x2 solve, flow written once.
+//   Every R0 / flow row is read once (no vertical halo), R1 gathers mostly hit L1/L2.
 //   Algorithmic HBM bytes per pixel: R0 20 + R1 20 + flow in 8 + flow out 8 = 56.
 // Compiled with -fmad=false: OpenCV's scalar code has no fused multiply-adds here.
 #include "fdn_internal.cuh"
@@ -20,61 +26,69 @@
 namespace fdn {
 
 struct FlowIterArgs {
-    const float* R;
-    int64_t R_stride;
+    const float* R;     // level base inside slot 0: [h*w] float4 (channels 0-3) then [h*w] float (channel 4)
+    int64_t R_stride;   // floats per slot
     SlotMap map0, map1;
     const float* flow_in;
     float* flow_out;
     int h, w, m;
-    double scale;  // 1 / winsize^2
+    int LS;             // shared tile line stride in doubles (== 1 mod 16)
+    int strips;
+    double scale;       // 1 / winsize^2
+    double* carry;      // [n][strips][h][5]
+    unsigned long long* flags;  // [n][strips]
+    unsigned long long epoch;
 };
 
-__device__ __forceinline__ void update_matrices_px(const float* __restrict__ R0, const float* __restrict__ R1,
+__device__ __forceinline__ void update_matrices_px(const float4* __restrict__ R0a, const float* __restrict__ R0b,
+                                                   const float4* __restrict__ R1a, const float* __restrict__ R1b,
                                                    const float2* __restrict__ flow, int x, int y, int h, int w,
                                                    float M[5])
 {
-    const float2 f = flow[(int64_t)y * w + x];
+    const int idx = y * w + x;
+    const float2 f = __ldg(flow + idx);
     const float dx = f.x, dy = f.y;
     float fx = __fadd_rn((float)x, dx), fy = __fadd_rn((float)y, dy);
     const int x1 = (int)floorf(fx), y1 = (int)floorf(fy);
     fx = __fsub_rn(fx, (float)x1);
     fy = __fsub_rn(fy, (float)y1);
-    const float* r0p = R0 + (int64_t)y * 5 * w + x;
-    const float c0 = r0p[0], c1 = r0p[w], c2 = r0p[2 * w], c3 = r0p[3 * w], c4 = r0p[4 * w];
+    const float4 c03 = __ldg(R0a + idx);
+    const float c4 = __ldg(R0b + idx);
     float r2, r3, r4, r5, r6;
     if ((unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1)) {
         const float ofx = __fsub_rn(1.f, fx), ofy = __fsub_rn(1.f, fy);
         const float a00 = __fmul_rn(ofx, ofy), a01 = __fmul_rn(fx, ofy), a10 = __fmul_rn(ofx, fy),
                     a11 = __fmul_rn(fx, fy);
-        const float* q0 = R1 + (int64_t)y1 * 5 * w + x1;
-        const float* q1 = q0 + 5 * w;
-#define FDN_BILIN(c)                                                                                         \
-    __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a00, q0[(c) * w]), __fmul_rn(a01, q0[(c) * w + 1])),             \
-                        __fmul_rn(a10, q1[(c) * w])),                                                        \
-              __fmul_rn(a11, q1[(c) * w + 1]))
-        r2 = FDN_BILIN(0);
-        r3 = FDN_BILIN(1);
-        r4 = FDN_BILIN(2);
-        r5 = FDN_BILIN(3);
-        r6 = FDN_BILIN(4);
+        const int g = y1 * w + x1;
+        const float4 p00 = __ldg(R1a + g), p01 = __ldg(R1a + g + 1), p10 = __ldg(R1a + g + w),
+                     p11 = __ldg(R1a + g + w + 1);
+        const float q00 = __ldg(R1b + g), q01 = __ldg(R1b + g + 1), q10 = __ldg(R1b + g + w),
+                    q11 = __ldg(R1b + g + w + 1);
+#define FDN_BILIN(v00, v01, v10, v11) \
+    __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a00, v00), __fmul_rn(a01, v01)), __fmul_rn(a10, v10)), __fmul_rn(a11, v11))
+        r2 = FDN_BILIN(p00.x, p01.x, p10.x, p11.x);
+        r3 = FDN_BILIN(p00.y, p01.y, p10.y, p11.y);
+        r4 = FDN_BILIN(p00.z, p01.z, p10.z, p11.z);
+        r5 = FDN_BILIN(p00.w, p01.w, p10.w, p11.w);
+        r6 = FDN_BILIN(q00, q01, q10, q11);
 #undef FDN_BILIN
-        r4 = __fmul_rn(__fadd_rn(c2, r4), 0.5f);
-        r5 = __fmul_rn(__fadd_rn(c3, r5), 0.5f);
+        r4 = __fmul_rn(__fadd_rn(c03.z, r4), 0.5f);
+        r5 = __fmul_rn(__fadd_rn(c03.w, r5), 0.5f);
         r6 = __fmul_rn(__fadd_rn(c4, r6), 0.25f);
     } else {
         r2 = r3 = 0.f;
-        r4 = c2;
-        r5 = c3;
+        r4 = c03.z;
+        r5 = c03.w;
         r6 = __fmul_rn(c4, 0.5f);
     }
-    r2 = __fmul_rn(__fsub_rn(c0, r2), 0.5f);
-    r3 = __fmul_rn(__fsub_rn(c1, r3), 0.5f);
+    r2 = __fmul_rn(__fsub_rn(c03.x, r2), 0.5f);
+    r3 = __fmul_rn(__fsub_rn(c03.y, r3), 0.5f);
     r2 = __fadd_rn(r2, __fadd_rn(__fmul_rn(r4, dy), __fmul_rn(r6, dx)));
     r3 = __fadd_rn(r3, __fadd_rn(__fmul_rn(r6, dy), __fmul_rn(r5, dx)));
     if ((unsigned)(x - 5) >= (unsigned)(w - 10) || (unsigned)(y - 5) >= (unsigned)(h - 10)) {
         // border[5] = {0.14, 0.14, 0.4472, 0.4472, 0.4472}
         float s = x < 5 ? (x < 2 ? 0.14f : 0.4472f) : 1.f;
-        int xr = w - x - 1, yr = h - y - 1;
+        const int xr = w - x - 1, yr = h - y - 1;
         s = __fmul_rn(s, x >= w - 5 ? (xr < 2 ? 0.14f : 0.4472f) : 1.f);
         s = __fmul_rn(s, y < 5 ? (y < 2 ? 0.14f : 0.4472f) : 1.f);
         s = __fmul_rn(s, y >= h - 5 ? (yr < 2 ? 0.14f : 0.4472f) : 1.f);
@@ -88,49 +102,60 @@ __device__ __forceinline__ void update_matrices_px(const float* __restrict__ R0,
     M[4] = __fadd_rn(__fmul_rn(r6, r2), __fmul_rn(r5, r3));
 }
 
-template <int CW>
+template <int CW, int TR>
 __global__ void __launch_bounds__(CW + 32)
 k_flow_iter(FlowIterArgs a)
 {
     constexpr int NT = CW + 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int m = a.m, h = a.h, w = a.w;
+    const int m = a.m, h = a.h, w = a.w, LS = a.LS;
     const int RR = 2 * m + 2;
-    double* vbuf = reinterpret_cast<double*>(smem_raw);                              // [2][5][NT]
-    float* ring = reinterpret_cast<float*>(smem_raw + sizeof(double) * 2 * 5 * NT);  // [RR][5][NT]
+    double* tile = reinterpret_cast<double*>(smem_raw);                               // [TR*5][LS]
+    float* ring = reinterpret_cast<float*>(smem_raw + sizeof(double) * TR * 5 * LS);  // [RR][5][NT]
 
     const int t = threadIdx.x;
-    const int b = blockIdx.y;
-    const int x0 = blockIdx.x * CW;
-    // position p in the strip's extended window [x0 - m, x0 + CW + m)
-    int p;
+    const int k = blockIdx.x;  // strip
+    const int b = blockIdx.y;  // image pair
+    const int x0 = k * CW;
+    // tile position q <-> column x0 - m - 1 + q, q in [0, CW + 2m + 1)
+    int q;
     bool active = true;
     if (t < CW) {
-        p = t + m;
+        q = t + m + 1;
     } else {
         const int hd = t - CW;
-        if (hd < m) p = hd;
-        else if (hd < 2 * m) p = CW + hd;
-        else { p = 0; active = false; }
+        if (hd < m + 1) q = hd;
+        else if (hd < 2 * m + 1) q = CW + hd;
+        else { q = 0; active = false; }
     }
-    const int xcl = min(max(x0 - m + p, 0), w - 1);
+    const int xcl = min(max(x0 - m - 1 + q, 0), w - 1);
     const bool core = (t < CW) && (x0 + t < w);
+    const int ncols = min(CW, w - x0);
 
     const float* R0 = a.R + (int64_t)a.map0.slot(b) * a.R_stride;
     const float* R1 = a.R + (int64_t)a.map1.slot(b) * a.R_stride;
+    const float4* R0a = reinterpret_cast<const float4*>(R0);
+    const float4* R1a = reinterpret_cast<const float4*>(R1);
+    const float* R0b = R0 + (int64_t)4 * h * w;
+    const float* R1b = R1 + (int64_t)4 * h * w;
     const float2* fin = reinterpret_cast<const float2*>(a.flow_in) + (int64_t)b * h * w;
     float2* fout = reinterpret_cast<float2*>(a.flow_out) + (int64_t)b * h * w;
+    double* carry_out = a.carry + ((int64_t)b * a.strips + k) * h * 5;
+    const double* carry_in = a.carry + ((int64_t)b * a.strips + max(k - 1, 0)) * h * 5;
+    volatile unsigned long long* flag_in = a.flags + (int64_t)b * a.strips + max(k - 1, 0);
+    volatile unsigned long long* flag_out = a.flags + (int64_t)b * a.strips + k;
 
     double vs[5] = {0, 0, 0, 0, 0};
-    int next_row = 0;   // next M row to compute
-    int next_slot = 0;  // its ring slot (= next_row mod RR)
+    int next_row = 0;       // next M row to compute
+    int next_slot = 0;      // its ring slot (= next_row mod RR)
+    int slot_old = 0;       // ring slot of row max(y-m-1, 0)
     float Mv[5];
 
     if (active) {
         // rows 0 .. m-1 (clamped to h-1) seed the column sums: vsum = M[0]*(m+2) + sum_{y=1}^{m-1} M[min(y,h-1)]
         const int last_init = min(max(m - 1, 0), h - 1);
         for (; next_row <= last_init; next_row++) {
-            update_matrices_px(R0, R1, fin, xcl, next_row, h, w, Mv);
+            update_matrices_px(R0a, R0b, R1a, R1b, fin, xcl, next_row, h, w, Mv);
 #pragma unroll
             for (int c = 0; c < 5; c++) ring[(next_slot * 5 + c) * NT + t] = Mv[c];
             next_slot = next_slot + 1 == RR ? 0 : next_slot + 1;
@@ -145,81 +170,169 @@ k_flow_iter(FlowIterArgs a)
         }
     }
 
-    for (int y = 0; y < h; y++) {
-        double* vb = vbuf + (y & 1) * 5 * NT;
+    int tile_idx = 0;
+    for (int y0 = 0; y0 < h; y0 += TR, tile_idx++) {
+        // ---------------- phase V: column sums of TR rows ----------------
         if (active) {
-            const int j1 = min(y + m, h - 1);
-            if (next_row <= j1) {  // exactly one new row per step while y + m < h
-                update_matrices_px(R0, R1, fin, xcl, next_row, h, w, Mv);
 #pragma unroll
-                for (int c = 0; c < 5; c++) ring[(next_slot * 5 + c) * NT + t] = Mv[c];
-                next_slot = next_slot + 1 == RR ? 0 : next_slot + 1;
-                next_row++;
+            for (int r = 0; r < TR; r++) {
+                const int y = y0 + r;
+                if (y < h) {
+                    const int j1 = min(y + m, h - 1);
+                    int s1;
+                    if (next_row <= j1) {  // exactly one new row per step while y + m < h
+                        update_matrices_px(R0a, R0b, R1a, R1b, fin, xcl, next_row, h, w, Mv);
+#pragma unroll
+                        for (int c = 0; c < 5; c++) ring[(next_slot * 5 + c) * NT + t] = Mv[c];
+                        s1 = next_slot;
+                        next_slot = next_slot + 1 == RR ? 0 : next_slot + 1;
+                        next_row++;
+                    } else {  // bottom border: row h-1 again (the last slot written)
+                        s1 = next_slot == 0 ? RR - 1 : next_slot - 1;
+#pragma unroll
+                        for (int c = 0; c < 5; c++) Mv[c] = ring[(s1 * 5 + c) * NT + t];
+                    }
+                    // row max(y-m-1, 0): slot_old advances once y-m-1 > 0
+#pragma unroll
+                    for (int c = 0; c < 5; c++) {
+                        const float d = __fsub_rn(Mv[c], ring[(slot_old * 5 + c) * NT + t]);
+                        vs[c] = __dadd_rn(vs[c], (double)d);
+                        tile[(r * 5 + c) * LS + q] = vs[c];
+                    }
+                    if (y >= m + 1) slot_old = slot_old + 1 == RR ? 0 : slot_old + 1;  // row max(y-m, 0) next
+                }
             }
-            const int j0 = max(y - m - 1, 0);
-            const int s1 = j1 % RR, s0 = j0 % RR;
-#pragma unroll
-            for (int c = 0; c < 5; c++) {
-                const float d = __fsub_rn(ring[(s1 * 5 + c) * NT + t], ring[(s0 * 5 + c) * NT + t]);
-                vs[c] = __dadd_rn(vs[c], (double)d);
-                vb[c * NT + p] = vs[c];
+        }
+        if (t == 0 && k > 0) {  // the left strip must have published this tile's carries
+            const unsigned long long want = a.epoch + (unsigned long long)tile_idx + 1ull;
+            while (*flag_in < want) __nanosleep(40);
+            __threadfence();
+        }
+        __syncthreads();
+        // ---------------- phase H: sequential horizontal running sums ----------------
+        if (t < 5 * TR) {
+            const int r = t / 5, c = t - r * 5;
+            const int y = y0 + r;
+            if (y < h) {
+                double* line = tile + (r * 5 + c) * LS;
+                double S;
+                if (k == 0) {
+                    // g = vsum[0]*(m+2) + vsum[1] + ... + vsum[m-1]   (columns clamp to the replicated border)
+                    S = __dmul_rn(line[m + 1], (double)(m + 2));
+                    for (int x = 1; x < m; x++) S = __dadd_rn(S, line[m + 1 + x]);
+                } else {
+                    S = __ldcg(carry_in + (int64_t)y * 5 + c);
+                }
+                const int off = 2 * m + 1;
+#pragma unroll 4
+                for (int i = 0; i < ncols; i++) {
+                    const double d = __dsub_rn(line[i + off], line[i]);
+                    S = __dadd_rn(S, d);
+                    line[i] = S;
+                }
+                if (k + 1 < a.strips) {
+                    __stcg(carry_out + (int64_t)y * 5 + c, S);
+                    __threadfence();
+                }
             }
         }
         __syncthreads();
+        if (t == 0 && k + 1 < a.strips) *flag_out = a.epoch + (unsigned long long)tile_idx + 1ull;
+        // ---------------- phase S: solve ----------------
         if (core) {
-            double g[5];
 #pragma unroll
-            for (int c = 0; c < 5; c++) {
-                const double* q = vb + c * NT + t;  // positions t .. t + 2m  <->  columns x-m .. x+m
-                double s = q[0];
-                for (int i = 1; i <= 2 * m; i++) s = __dadd_rn(s, q[i]);
-                g[c] = __dmul_rn(s, a.scale);
+            for (int r = 0; r < TR; r++) {
+                const int y = y0 + r;
+                if (y < h) {
+                    double g[5];
+#pragma unroll
+                    for (int c = 0; c < 5; c++) g[c] = __dmul_rn(tile[(r * 5 + c) * LS + t], a.scale);
+                    const double det = __dadd_rn(__dsub_rn(__dmul_rn(g[0], g[2]), __dmul_rn(g[1], g[1])), 1e-3);
+                    const double idet = __ddiv_rn(1., det);
+                    float2 o;
+                    o.x = (float)__dmul_rn(__dsub_rn(__dmul_rn(g[0], g[4]), __dmul_rn(g[1], g[3])), idet);
+                    o.y = (float)__dmul_rn(__dsub_rn(__dmul_rn(g[2], g[3]), __dmul_rn(g[1], g[4])), idet);
+                    fout[y * w + x0 + t] = o;
+                }
             }
-            const double det = __dadd_rn(__dsub_rn(__dmul_rn(g[0], g[2]), __dmul_rn(g[1], g[1])), 1e-3);
-            const double idet = __ddiv_rn(1., det);
-            float2 o;
-            o.x = (float)__dmul_rn(__dsub_rn(__dmul_rn(g[0], g[4]), __dmul_rn(g[1], g[3])), idet);
-            o.y = (float)__dmul_rn(__dsub_rn(__dmul_rn(g[2], g[3]), __dmul_rn(g[1], g[4])), idet);
-            fout[(int64_t)y * w + x0 + t] = o;
         }
+        __syncthreads();
     }
 }
 
-int launch_flow_iter(const float* R, int64_t R_stride, SlotMap map0, SlotMap map1, const float* flow_in,
-                     float* flow_out, int n, int h, int w, int winsize, cudaStream_t st)
+static unsigned long long g_flow_epoch = 1;
+
+// Scratch layout: [flags: n * MAX_STRIPS u64][carries: n * strips * h * 5 f64]. The flag area has the same place
+// and size for every pyramid level that shares the scratch (it only ever holds epochs of earlier launches, which
+// compare below the current one); the carry area is rewritten by every launch before it is read.
+#define FDN_MAX_STRIPS 64
+
+size_t flow_iter_scratch_bytes(int n, int h, int w)
 {
-    FDN_CHECK_ARG(winsize >= 1 && winsize <= 33, "winsize %d unsupported (1..33)", winsize);
+    const int CW = w > 96 ? 128 : 32;
+    const size_t strips = (size_t)cdiv(w, CW);
+    const size_t carry = sizeof(double) * 5 * (size_t)n * strips * h;
+    const size_t flags = sizeof(unsigned long long) * (size_t)n * FDN_MAX_STRIPS;
+    return ((carry + 255) / 256) * 256 + ((flags + 255) / 256) * 256;
+}
+
+int flow_iter_scratch_init(void* scratch, size_t bytes, cudaStream_t st)
+{
+    // flags must start below every epoch; carries need no initialisation
+    FDN_CUDA(cudaMemsetAsync(scratch, 0, bytes, st));
+    return FDN_OK;
+}
+
+int launch_flow_iter(const float* R, int64_t R_stride, SlotMap map0, SlotMap map1, const float* flow_in,
+                     float* flow_out, int n, int h, int w, int winsize, void* scratch, size_t scratch_bytes,
+                     cudaStream_t st)
+{
+    FDN_CHECK_ARG(winsize >= 1 && winsize <= 31, "winsize %d unsupported (1..31)", winsize);
     FDN_CHECK_ARG(flow_in != flow_out, "flow_in and flow_out must not alias");
+    FDN_CHECK_ARG((int64_t)h * w < (1ll << 28), "level image too large");
+    FDN_CHECK_ARG(scratch && scratch_bytes >= flow_iter_scratch_bytes(n, h, w), "flow iteration scratch too small");
+    constexpr int TR = 4;
     FlowIterArgs a;
-    a.R = R; a.R_stride = R_stride; a.flow_in = flow_in; a.flow_out = flow_out;
+    a.R = R; a.R_stride = R_stride;
     a.h = h; a.w = w; a.m = winsize / 2;
     a.scale = 1. / ((double)winsize * winsize);
     const int RR = 2 * a.m + 2;
     const bool wide = w > 96;
-    const int NT = (wide ? 128 : 32) + 32;
-    const size_t smem = sizeof(double) * 2 * 5 * NT + sizeof(float) * RR * 5 * NT;
+    const int CW = wide ? 128 : 32;
+    const int NT = CW + 32;
+    a.strips = (int)cdiv(w, CW);
+    int LS = CW + 2 * a.m + 2;
+    while (LS % 16 != 1) LS++;
+    a.LS = LS;
+    // flags first (fixed place and size), carries behind them; a smaller level fits into the level-0 scratch
+    FDN_CHECK_ARG(a.strips <= FDN_MAX_STRIPS, "image too wide (%d strips)", a.strips);
+    const size_t flag_bytes = ((sizeof(unsigned long long) * (size_t)n * FDN_MAX_STRIPS + 255) / 256) * 256;
+    a.flags = static_cast<unsigned long long*>(scratch);
+    a.carry = reinterpret_cast<double*>(static_cast<char*>(scratch) + flag_bytes);
+    const size_t smem = sizeof(double) * TR * 5 * LS + sizeof(float) * RR * 5 * NT;
     static bool attr_set = false;
     if (!attr_set) {
-        FDN_CUDA(cudaFuncSetAttribute(k_flow_iter<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        FDN_CUDA(cudaFuncSetAttribute(k_flow_iter<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        FDN_CUDA(cudaFuncSetAttribute(k_flow_iter<128, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        FDN_CUDA(cudaFuncSetAttribute(k_flow_iter<32, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set = true;
     }
+    const unsigned long long tiles = (unsigned long long)cdiv(h, TR);
     for (int b0 = 0; b0 < n; b0 += 65535) {
         const int nb = n - b0 < 65535 ? n - b0 : 65535;
         a.map0 = map0; a.map0.base += b0;
         a.map1 = map1; a.map1.base += b0;
         a.flow_in = flow_in + (int64_t)b0 * h * w * 2;
         a.flow_out = flow_out + (int64_t)b0 * h * w * 2;
+        a.epoch = g_flow_epoch;
         ProfScope ps(K_FLOW_ITER, 56.0 * nb * h * w, st);
-        if (wide) {
-            dim3 grid((unsigned)cdiv(w, 128), (unsigned)nb);
-            k_flow_iter<128><<<grid, 160, smem, st>>>(a);
-        } else {
-            dim3 grid((unsigned)cdiv(w, 32), (unsigned)nb);
-            k_flow_iter<32><<<grid, 64, smem, st>>>(a);
-        }
+        dim3 grid((unsigned)a.strips, (unsigned)nb);
+        if (wide) k_flow_iter<128, TR><<<grid, 160, smem, st>>>(a);
+        else k_flow_iter<32, TR><<<grid, 64, smem, st>>>(a);
         FDN_LAUNCHED("k_flow_iter");
+        a.carry += (int64_t)nb * a.strips * h * 5;
+        a.flags += (int64_t)nb * a.strips;
     }
+    g_flow_epoch += tiles + 1;
     return FDN_OK;
 }
 

@@ -6,6 +6,7 @@
 // fused, float32 vs float64) follows OpenCV so that results are bit-identical to the CPU reference on
 // AVX2 hosts; this file is compiled with -fmad=false and fuses only where fmaf() is written.
 #include <math.h>
+#include <string.h>
 
 #include "fdn_internal.cuh"
 
@@ -64,13 +65,45 @@ void prepare_poly_consts(int n, double sigma, PolyConsts* pc)
             G33 += gg * x * x * x * x;
             G55 += gg * x * x * y * y;
         }
-    double a = G00, b = G11, c = G33, d = G55;
-    double det3 = a * (c * c - d * d) - b * (b * c - b * d) + b * (b * d - b * c);
+    // cv::invert(G, DECOMP_CHOLESKY): OpenCV's CholImpl on an identity right-hand side, operation by operation
+    // (a closed-form inverse differs in the last bit of ig03/ig33 and flips ~1 float32 rounding of R in 1e7)
+    enum { m = 6 };
+    double L[6][6], inv[6][6];
+    memset(L, 0, sizeof L);
+    L[0][0] = G00; L[1][1] = G11; L[3][3] = G33; L[5][5] = G55;
+    L[2][2] = L[0][3] = L[0][4] = L[3][0] = L[4][0] = L[1][1];
+    L[4][4] = L[3][3];
+    L[3][4] = L[4][3] = L[5][5];
+    for (int i = 0; i < m; i++)
+        for (int j = 0; j < m; j++) inv[i][j] = i == j ? 1. : 0.;
+    for (int i = 0; i < m; i++) {
+        double t;
+        for (int j = 0; j < i; j++) {
+            t = L[i][j];
+            for (int k = 0; k < j; k++) t -= L[i][k] * L[j][k];
+            L[i][j] = t * L[j][j];
+        }
+        t = L[i][i];
+        for (int k = 0; k < i; k++) { double u = L[i][k]; t -= u * u; }
+        L[i][i] = 1. / sqrt(t);
+    }
+    for (int i = 0; i < m; i++)
+        for (int j = 0; j < m; j++) {
+            double t = inv[i][j];
+            for (int k = 0; k < i; k++) t -= L[i][k] * inv[k][j];
+            inv[i][j] = t * L[i][i];
+        }
+    for (int i = m - 1; i >= 0; i--)
+        for (int j = 0; j < m; j++) {
+            double t = inv[i][j];
+            for (int k = m - 1; k > i; k--) t -= L[k][i] * inv[k][j];
+            inv[i][j] = t * L[i][i];
+        }
     pc->n = n;
-    pc->ig11 = 1. / b;
-    pc->ig55 = 1. / d;
-    pc->ig03 = -(b * c - b * d) / det3;
-    pc->ig33 = (a * c - b * b) / det3;
+    pc->ig11 = inv[1][1];
+    pc->ig03 = inv[0][3];
+    pc->ig33 = inv[3][3];
+    pc->ig55 = inv[5][5];
     for (int k = 0; k < 8; k++) { pc->g[k] = pc->xg[k] = pc->xxg[k] = 0.f; }
     for (int k = 0; k <= n; k++) { pc->g[k] = g[n + k]; pc->xg[k] = xg[n + k]; pc->xxg[k] = xxg[n + k]; }
 }
@@ -218,7 +251,7 @@ int launch_resize_linear_img(const float* in, int n, int H, int W, float* out, i
 // ------------------------------------------------------------------------------------------------
 // Stage 2: FarnebackPolyExp. Tile of PT x PT outputs per block, input tile with a poly_n halo staged in shared
 // memory (replicate border = clamped loads), float32 vertical moments for PT + 2n columns, float64 horizontal
-// pass. Output layout (h, 5, w).
+// pass. Output layout: [h*w] float4 (channels 0-3) followed by [h*w] float (channel 4).
 // ------------------------------------------------------------------------------------------------
 #define PT 32
 #define PN_MAX 7
@@ -275,12 +308,14 @@ k_polyexp(const float* __restrict__ img, int64_t img_stride, float* __restrict__
             b6 = __dadd_rn(b6, (double)__fmul_rn(__fsub_rn(r1[k], r1[-k]), pc.xg[k]));
             b5 = __dadd_rn(b5, (double)__fmul_rn(__fadd_rn(r2[k], r2[-k]), g0));
         }
-        float* dst = R + (int64_t)R_map.slot(b) * R_stride + (int64_t)gy * 5 * w + gx;
-        dst[0] = (float)__dmul_rn(b3, pc.ig11);
-        dst[(int64_t)w] = (float)__dmul_rn(b2, pc.ig11);
-        dst[(int64_t)2 * w] = (float)__dadd_rn(__dmul_rn(b1, pc.ig03), __dmul_rn(b5, pc.ig33));
-        dst[(int64_t)3 * w] = (float)__dadd_rn(__dmul_rn(b1, pc.ig03), __dmul_rn(b4, pc.ig33));
-        dst[(int64_t)4 * w] = (float)__dmul_rn(b6, pc.ig55);
+        float* dst = R + (int64_t)R_map.slot(b) * R_stride;
+        float4 o;
+        o.x = (float)__dmul_rn(b3, pc.ig11);
+        o.y = (float)__dmul_rn(b2, pc.ig11);
+        o.z = (float)__dadd_rn(__dmul_rn(b1, pc.ig03), __dmul_rn(b5, pc.ig33));
+        o.w = (float)__dadd_rn(__dmul_rn(b1, pc.ig03), __dmul_rn(b4, pc.ig33));
+        reinterpret_cast<float4*>(dst)[(int64_t)gy * w + gx] = o;
+        dst[(int64_t)4 * h * w + (int64_t)gy * w + gx] = (float)__dmul_rn(b6, pc.ig55);
     }
 }
 

@@ -181,37 +181,84 @@ int launch_gauss_rows(const float* in, float* out, int64_t rows, int W, const do
 }
 
 // ------------------------------------------------------------------------------------------------
-// Batched transpose of the last two axes: in [n][A][B] -> out [n][B][A]  (32x32 shared-memory tiles)
+// Batched transpose of the last two axes with arbitrary outer/row strides (32x32 shared-memory tiles):
+//   out[n*out_sn + b*out_sb + a] = in[n*in_sn + a*in_sa + b],  a < A, b < B
+// Dense case ([n][A][B] -> [n][B][A]): in_sn = out_sn = A*B, in_sa = B, out_sb = A. The strided form is the
+// transposing unpack of the multi-GPU re-slab (flowdenoising_b200/dist.py).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-k_transpose(const float* __restrict__ in, float* __restrict__ out, int A, int B)
+k_transpose(const float* __restrict__ in, int64_t in_sn, int64_t in_sa, float* __restrict__ out, int64_t out_sn,
+            int64_t out_sb, int A, int B)
 {
     __shared__ float tile[32][33];
     const int64_t img = blockIdx.z;
     const int b0 = blockIdx.x * 32, a0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
-    const float* src = in + img * (int64_t)A * B;
-    float* dst = out + img * (int64_t)A * B;
+    const float* src = in + img * in_sn;
+    float* dst = out + img * out_sn;
     for (int i = ty; i < 32; i += 8) {
         int a = a0 + i, b = b0 + tx;
-        if (a < A && b < B) tile[i][tx] = src[(int64_t)a * B + b];
+        if (a < A && b < B) tile[i][tx] = src[(int64_t)a * in_sa + b];
     }
     __syncthreads();
     for (int i = ty; i < 32; i += 8) {
         int b = b0 + i, a = a0 + tx;
-        if (a < A && b < B) dst[(int64_t)b * A + a] = tile[tx][i];
+        if (a < A && b < B) dst[(int64_t)b * out_sb + a] = tile[tx][i];
     }
 }
 
-int launch_transpose(const float* in, float* out, int n, int A, int B, cudaStream_t st)
+int launch_transpose_strided(const float* in, int64_t in_sn, int64_t in_sa, float* out, int64_t out_sn, int64_t out_sb,
+                             int n, int A, int B, cudaStream_t st)
 {
     FDN_CHECK_ARG(cdiv(A, 32) <= 65535, "transpose: A too large");
     for (int b0 = 0; b0 < n; b0 += 65535) {
         const int nb = n - b0 < 65535 ? n - b0 : 65535;
         dim3 grid((unsigned)cdiv(B, 32), (unsigned)cdiv(A, 32), (unsigned)nb);
         ProfScope ps(K_TRANSPOSE, 8.0 * nb * A * B, st);
-        k_transpose<<<grid, 256, 0, st>>>(in + (int64_t)b0 * A * B, out + (int64_t)b0 * A * B, A, B);
+        k_transpose<<<grid, 256, 0, st>>>(in + (int64_t)b0 * in_sn, in_sn, in_sa, out + (int64_t)b0 * out_sn, out_sn,
+                                          out_sb, A, B);
         FDN_LAUNCHED("k_transpose");
+    }
+    return FDN_OK;
+}
+
+int launch_transpose(const float* in, float* out, int n, int A, int B, cudaStream_t st)
+{
+    return launch_transpose_strided(in, (int64_t)A * B, B, out, (int64_t)A * B, A, n, A, B, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Strided 3-D copy with periodic index offsets (the packing side of the re-slab / halo exchange):
+//   out[a*out_sa + b*out_sb + c] = in[a*in_sa + ((b0 + b) mod bw)*in_sb + ((c0 + c) mod cw)]
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_copy3d(const float* __restrict__ in, int64_t in_sa, int64_t in_sb, int b0, int bw, int c0, int cw,
+         float* __restrict__ out, int64_t out_sa, int64_t out_sb, int B, int C)
+{
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    const int b = blockIdx.y;
+    const int64_t a = blockIdx.z;
+    if (c >= C) return;
+    int bi = (b0 + b) % bw;
+    if (bi < 0) bi += bw;
+    int ci = (c0 + c) % cw;
+    if (ci < 0) ci += cw;
+    (void)B;
+    out[a * out_sa + (int64_t)b * out_sb + c] = in[a * in_sa + (int64_t)bi * in_sb + ci];
+}
+
+int launch_copy3d(const float* in, int64_t in_sa, int64_t in_sb, int b0, int bw, int c0, int cw, float* out,
+                  int64_t out_sa, int64_t out_sb, int A, int B, int C, cudaStream_t st)
+{
+    FDN_CHECK_ARG(B <= 65535, "copy3d: B too large");
+    FDN_CHECK_ARG(bw >= 1 && cw >= 1, "copy3d: wrap lengths must be >= 1");
+    for (int a0 = 0; a0 < A; a0 += 65535) {
+        const int na = A - a0 < 65535 ? A - a0 : 65535;
+        dim3 grid((unsigned)cdiv(C, 256), (unsigned)B, (unsigned)na);
+        ProfScope ps(K_COPY3D, 8.0 * na * B * C, st);
+        k_copy3d<<<grid, 256, 0, st>>>(in + (int64_t)a0 * in_sa, in_sa, in_sb, b0, bw, c0, cw,
+                                       out + (int64_t)a0 * out_sa, out_sa, out_sb, B, C);
+        FDN_LAUNCHED("k_copy3d");
     }
     return FDN_OK;
 }

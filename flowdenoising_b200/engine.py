@@ -153,6 +153,26 @@ class DeviceEngine:
             _lib.check(self.lib.fdn_transpose_yx(src.data_ptr(), dst.data_ptr(), n, A, B, _stream_ptr(torch)))
         return dst
 
+    def empty(self, shape):
+        return self.torch.empty(tuple(int(s) for s in shape), dtype=self.torch.float32, device=self.device)
+
+    def copy3d(self, src, src_off, in_sa, in_sb, b0, bw, c0, cw, dst, dst_off, out_sa, out_sb, A, B, C):
+        """dst[a*out_sa + b*out_sb + c] = src[a*in_sa + ((b0+b) % bw)*in_sb + (c0+c) % cw]  (element offsets/strides
+        into flat float32 buffers) -- the packing kernel of the multi-GPU re-slab."""
+        torch = self.torch
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.fdn_copy3d(src.data_ptr() + 4 * int(src_off), int(in_sa), int(in_sb), int(b0), int(bw),
+                                           int(c0), int(cw), dst.data_ptr() + 4 * int(dst_off), int(out_sa),
+                                           int(out_sb), int(A), int(B), int(C), _stream_ptr(torch)))
+
+    def transpose_strided(self, src, src_off, in_sn, in_sa, dst, dst_off, out_sn, out_sb, n, A, B):
+        """dst[i*out_sn + b*out_sb + a] = src[i*in_sn + a*in_sa + b] -- the transposing unpack of the re-slab."""
+        torch = self.torch
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.fdn_transpose_strided(src.data_ptr() + 4 * int(src_off), int(in_sn), int(in_sa),
+                                                      dst.data_ptr() + 4 * int(dst_off), int(out_sn), int(out_sb),
+                                                      int(n), int(A), int(B), _stream_ptr(torch)))
+
     def filter_along_axis(self, vol, out, axis: int, kernel, flow: Optional[FlowParams], chunk: Optional[int] = None,
                           exact: bool = True, scratch=None):
         """One pass of the reference's filter_along_{Z,Y,X} (src/flowdenoising.py:175-283) on the device."""

@@ -24,8 +24,9 @@
  *                   slice_stride=X,row_stride=Y*X; X pass runs on the [Z][X][Y] transpose (fdn_transpose_yx).
  *   image         : dense row-major (h, w)
  *   flow          : dense (h, w, 2), x component first  (same as OpenCV CV_32FC2)
- *   R (polyexp)   : dense (h, 5, w): row-interleaved channel planes, channel order as OpenCV
- *                   (R0=d/dy, R1=d/dx, R2=yy, R3=xx, R4=xy)  -- NOT OpenCV's (h, w, 5)
+ *   R (polyexp)   : per image [h*w] float4 holding channels 0-3 followed by [h*w] float holding channel 4 (padded
+ *                   to 16 bytes; fdn_polyexp_floats(h, w) floats in total), channel order as OpenCV
+ *                   (R0=d/dy, R1=d/dx, R2=yy, R3=xx, R4=xy)  -- NOT OpenCV's interleaved (h, w, 5)
  */
 #ifndef FDN_B200_H
 #define FDN_B200_H
@@ -112,17 +113,30 @@ int fdn_gauss_rows(const float* d_in, float* d_out, int64_t n_rows, int W, const
 /* Batched 2-D transpose of the last two axes: in [n][A][B] -> out [n][B][A]. */
 int fdn_transpose_yx(const float* d_in, float* d_out, int n, int A, int B, void* stream);
 
+/* Strided variants used by the multi-GPU re-slab (flowdenoising_b200/dist.py):
+ *   fdn_transpose_strided: out[n*out_sn + b*out_sb + a] = in[n*in_sn + a*in_sa + b]           (a < A, b < B)
+ *   fdn_copy3d           : out[a*out_sa + b*out_sb + c] = in[a*in_sa + ((b0+b) mod b_wrap)*in_sb + ((c0+c) mod c_wrap)]
+ * (the periodic offsets pack a slab together with its wrap-around halo, src/flowdenoising.py:312 `% shape`). */
+int fdn_transpose_strided(const float* d_in, int64_t in_sn, int64_t in_sa, float* d_out, int64_t out_sn, int64_t out_sb,
+                          int n, int A, int B, void* stream);
+int fdn_copy3d(const float* d_in, int64_t in_sa, int64_t in_sb, int b0, int b_wrap, int c0, int c_wrap, float* d_out,
+               int64_t out_sa, int64_t out_sb, int A, int B, int C, void* stream);
+
 /* ---- stage entry points (parity tests; all operate on a batch of `n` dense images) ---- */
 /* Stage 1: Gaussian pyramid level: GaussianBlur(full-res, ksz, sigma) then bilinear resize to (h, w).
  * d_tmp: scratch of 2*n*H*W floats. Input images: view-strided (slice_stride/row_stride as in fdn_view). */
 int fdn_pyramid_level(const float* d_img, int n, int H, int W, int64_t slice_stride, int64_t row_stride,
                       int ksz, double sigma, int h, int w, float* d_tmp, float* d_out, void* stream);
-/* Stage 2: polynomial expansion (h, w) -> R (h, 5, w). */
+/* Stage 2: polynomial expansion (h, w) -> R. One R image occupies fdn_polyexp_floats(h, w) floats. */
+size_t fdn_polyexp_floats(int h, int w);
 int fdn_polyexp(const float* d_img, int n, int h, int w, int poly_n, double poly_sigma, float* d_R, void* stream);
 /* Stage 3: one displacement-update iteration: M = UpdateMatrices(R0, R1, flow_in); flow_out =
- * BlurSolve(M, winsize). R0/R1: n images each (h, 5, w); flow_in/out: (n, h, w, 2), must not alias. */
+ * BlurSolve(M, winsize). R0/R1: n images each (fdn_polyexp_floats layout), R1 - R0 a whole number of images;
+ * flow_in/out: (n, h, w, 2), must not alias. d_scratch: fdn_flow_iteration_scratch_bytes(n, h, w) bytes (the
+ * inter-strip carries of the exact horizontal running sum). */
+size_t fdn_flow_iteration_scratch_bytes(int n, int h, int w);
 int fdn_flow_iteration(const float* d_R0, const float* d_R1, const float* d_flow_in, float* d_flow_out, int n,
-                       int h, int w, int winsize, void* stream);
+                       int h, int w, int winsize, void* d_scratch, size_t scratch_bytes, void* stream);
 /* Flow resampling between levels: INTER_AREA down-scale * scale (initial flow, coarsest level) and
  * INTER_LINEAR up-scale * 2 (next finer level). */
 int fdn_flow_area_down(const float* d_flow, int n, int H, int W, float* d_out, int h, int w, float scale,

@@ -345,9 +345,42 @@ typedef struct {
     double ig11, ig03, ig33, ig55;
 } polyexp_consts_t;
 
-/* Inverse of the 6x6 Gram matrix restricted to the four entries OpenCV uses.
-   G = [[a,0,0,b,b,0],[0,b,0,0,0,0],[0,0,b,0,0,0],[b,0,0,c,d,0],[b,0,0,d,c,0],[0,0,0,0,0,d]]
-   (OpenCV inverts it numerically with Cholesky; closed form differs by ~1e-16 relative). */
+/* cv::invert(G, DECOMP_CHOLESKY) for the 6x6 float64 Gram matrix: OpenCV's own CholImpl (hal::Cholesky64f falls
+   through to it for small matrices) applied to an identity right-hand side. Reproduced operation by operation:
+   a closed-form inverse differs in the last bit of ig03 / ig33, which flips the float32 rounding of one R value
+   in ~1e7 (enough to show up against cv2 on large images) [probe, round 1]. */
+static void chol_inv6(const double G[6][6], double inv[6][6])
+{
+    enum { m = 6 };
+    double L[6][6], b[6][6];
+    for (int i = 0; i < m; i++)
+        for (int j = 0; j < m; j++) { L[i][j] = G[i][j]; b[i][j] = i == j ? 1. : 0.; }
+    for (int i = 0; i < m; i++) {
+        double s;
+        for (int j = 0; j < i; j++) {
+            s = L[i][j];
+            for (int k = 0; k < j; k++) s -= L[i][k] * L[j][k];
+            L[i][j] = s * L[j][j];
+        }
+        s = L[i][i];
+        for (int k = 0; k < i; k++) { double t = L[i][k]; s -= t * t; }
+        L[i][i] = 1. / sqrt(s);
+    }
+    for (int i = 0; i < m; i++)
+        for (int j = 0; j < m; j++) {
+            double s = b[i][j];
+            for (int k = 0; k < i; k++) s -= L[i][k] * b[k][j];
+            b[i][j] = s * L[i][i];
+        }
+    for (int i = m - 1; i >= 0; i--)
+        for (int j = 0; j < m; j++) {
+            double s = b[i][j];
+            for (int k = m - 1; k > i; k--) s -= L[k][i] * b[k][j];
+            b[i][j] = s * L[i][i];
+        }
+    memcpy(inv, b, sizeof b);
+}
+
 static void polyexp_prepare(int n, double sigma, polyexp_consts_t* pc)
 {
     if (sigma < FLT_EPSILON) sigma = n * 0.3;
@@ -372,13 +405,17 @@ static void polyexp_prepare(int n, double sigma, polyexp_consts_t* pc)
             G33 += gg * x * x * x * x;
             G55 += gg * x * x * y * y;
         }
-    /* blocks: {1},{2},{5} are diagonal; {0,3,4} is [[a,b,b],[b,c,d],[b,d,c]] */
-    double a = G00, b = G11, c = G33, d = G55;
-    double det3 = a * (c * c - d * d) - b * (b * c - b * d) + b * (b * d - b * c);
-    pc->ig11 = 1. / b;
-    pc->ig55 = 1. / d;
-    pc->ig03 = -(b * c - b * d) / det3;           /* cofactor(3,0)/det, symmetric */
-    pc->ig33 = (a * c - b * b) / det3;
+    double G[6][6], inv[6][6];
+    memset(G, 0, sizeof G);
+    G[0][0] = G00; G[1][1] = G11; G[3][3] = G33; G[5][5] = G55;
+    G[2][2] = G[0][3] = G[0][4] = G[3][0] = G[4][0] = G[1][1];
+    G[4][4] = G[3][3];
+    G[3][4] = G[4][3] = G[5][5];
+    chol_inv6(G, inv);
+    pc->ig11 = inv[1][1];
+    pc->ig03 = inv[0][3];
+    pc->ig33 = inv[3][3];
+    pc->ig55 = inv[5][5];
     pc->n = n;
     for (int k = 0; k <= n; k++) { pc->g[k] = g[n + k]; pc->xg[k] = xg[n + k]; pc->xxg[k] = xxg[n + k]; }
 }

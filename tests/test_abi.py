@@ -58,6 +58,8 @@ def test_workspace_grows_with_chunk():
     a = lib.fdn_workspace_bytes(C.byref(v), 17, C.byref(p), 8)
     b = lib.fdn_workspace_bytes(C.byref(v), 17, C.byref(p), 0)
     assert 0 < a < b
-    # all 64 slices cached once: R = 64 slots * 5 * (256^2 + 128^2 + 64^2 + 32^2) floats, + 3 flow buffers
+    # all 64 slices cached once: R = 64 slots * 5 * (256^2 + 128^2 + 64^2 + 32^2) floats, + 3 flow buffers,
+    # + the carries/flags of the exact horizontal running sum (2 strips of 128 columns per image)
     R = 64 * 5 * (256 * 256 + 128 * 128 + 64 * 64 + 32 * 32) * 4
-    assert b == R + 3 * (64 * 256 * 256 * 2 * 4)
+    carries = 64 * 2 * 256 * 5 * 8 + 64 * 64 * 8
+    assert b == R + 3 * (64 * 256 * 256 * 2 * 4) + carries

@@ -2,9 +2,10 @@
 (tests/golden, produced by the unmodified reference) and the CPU oracle.
 
 North-star tolerances (BASELINE.json): OF path PSNR >= 50 dB and max|d| <= 1e-3 * data range; no-OF path <= 1-ulp
-scale. What is asserted here is tighter: the no-OF path is bit-exact, the OF path is bit-exact except for a
-bounded number of isolated voxels (a last-ulp flow difference that crosses a 1/32-px bin of cv2.remap's map
-quantiser moves one voxel by up to contrast/32 * tap weight; SURVEY.md §7 "hard parts").
+scale. What is asserted here is tighter: both paths are BIT-IDENTICAL to the reference's output (fixtures produced by
+the unmodified reference with cv2 4.13.0 on an AVX2 x86 host). Anything less would not be stable: a last-ulp flow
+difference that crosses a 1/32-px bin of cv2.remap's map quantiser moves a voxel by up to contrast/32 * tap weight
+(SURVEY.md §7 "hard parts"), which is how a merely "close" Farneback breaks the 1e-3 bound on noisy data.
 """
 import ctypes as C
 import hashlib
@@ -41,9 +42,9 @@ def report(name, got, ref, data_range=255.0):
 
 def check_of(name, got, ref, data_range=255.0):
     p, dmax, frac = report(name, got, ref, data_range)
-    assert p >= 50.0                       # north star
-    assert dmax <= 1e-3                    # north star
-    assert p >= 100.0 and frac >= 0.999    # this implementation
+    assert p >= 50.0                       # north star: PSNR >= 50 dB
+    assert dmax <= 1e-3                    # north star: max|d| <= 1e-3 of the data range
+    assert frac == 1.0                     # this implementation: bit-identical to the reference
 
 
 @pytest.mark.parametrize("name", ["toy_noof.npz", "toy_noof_float.npz"])
@@ -155,7 +156,8 @@ def test_cfg1_vs_reference_slices(eng, golden):
     zy, zyx = eng.filter(d_in, [k, k, k], p)
     got = zyx.cpu().numpy()
     check_of("cfg1 ZYX", got[zs], g["ZYX"])
-    print("cfg1 sha256 equal to reference:", hashlib.sha256(got.tobytes()).hexdigest() == str(g["sha_ZYX"]))
+    assert hashlib.sha256(got.tobytes()).hexdigest() == str(g["sha_ZYX"])      # whole volume, not just the slices
+    assert hashlib.sha256(zy.cpu().numpy().tobytes()).hexdigest() == str(g["sha_ZY"])
     assert abs(float(got.astype(np.float64).mean()) - float(g["mean_ZYX"])) < 1e-4
 
 

@@ -26,12 +26,25 @@ def dev(a):
     return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).cuda()
 
 
-def R_to_oracle_layout(R):   # (n, h, 5, w) -> (n, h, w, 5)
-    return np.ascontiguousarray(np.transpose(R, (0, 1, 3, 2)))
+def R_floats(h, w):
+    p = h * w
+    return 4 * p + (p + 3) // 4 * 4
 
 
-def R_from_oracle_layout(R):  # (n, h, w, 5) -> (n, h, 5, w)
-    return np.ascontiguousarray(np.transpose(R, (0, 1, 3, 2)))
+def R_to_oracle_layout(R, h, w):   # library layout (n, R_floats): [h*w] float4 + [h*w] float  ->  (n, h, w, 5)
+    n = R.shape[0]
+    out = np.empty((n, h, w, 5), np.float32)
+    out[..., :4] = R[:, :4 * h * w].reshape(n, h, w, 4)
+    out[..., 4] = R[:, 4 * h * w:5 * h * w].reshape(n, h, w)
+    return out
+
+
+def R_from_oracle_layout(R):  # (n, h, w, 5) -> (n, R_floats)
+    n, h, w, _ = R.shape
+    out = np.zeros((n, R_floats(h, w)), np.float32)
+    out[:, :4 * h * w] = R[..., :4].reshape(n, -1)
+    out[:, 4 * h * w:5 * h * w] = R[..., 4].reshape(n, -1)
+    return out
 
 
 def images(shape, n, seed):
@@ -81,20 +94,20 @@ def test_polyexp_bit_exact(eng, shape, poly):
     n = 2
     imgs = images(shape, n, 3) * np.float32(0.731)
     h, w = shape
-    R = torch.empty((n, h, 5, w), dtype=torch.float32, device="cuda")
+    assert eng.lib.fdn_polyexp_floats(h, w) == R_floats(h, w)
+    R = torch.zeros((n, R_floats(h, w)), dtype=torch.float32, device="cuda")
     rc = eng.lib.fdn_polyexp(dev(imgs).data_ptr(), n, h, w, poly[0], poly[1], R.data_ptr(), None)
     assert rc == 0, eng.lib.fdn_last_error()
-    got = R_to_oracle_layout(R.cpu().numpy())
+    got = R_to_oracle_layout(R.cpu().numpy(), h, w)
     for i in range(n):
         ref = O.polyexp(imgs[i], poly[0], poly[1])
         assert np.array_equal(got[i], ref), f"max|d|={np.abs(got[i] - ref).max()}"
 
 
-@pytest.mark.parametrize("shape", SHAPES + [(40, 300)])
+@pytest.mark.parametrize("shape", SHAPES + [(40, 300), (9, 520)])
 @pytest.mark.parametrize("win", [5, 9, 15])
 def test_flow_iteration(eng, shape, win):
-    """Stage 3: UpdateMatrices + box blur + solve. The only licence taken vs OpenCV is the float64 summation order
-    of the (2m+1)-wide horizontal window (direct sum vs sliding sum): <= 1e-6 px, >= 99.9 % of values bit-equal."""
+    """Stage 3: UpdateMatrices + box blur + solve, both running sums reproduced exactly -> bit-exact."""
     n = 2
     h, w = shape
     imgs = images(shape, 2 * n, 4)
@@ -105,16 +118,17 @@ def test_flow_iteration(eng, shape, win):
     dR = dev(R_from_oracle_layout(R))
     dflow = dev(flow)
     out = torch.empty_like(dflow)
+    nscr = eng.lib.fdn_flow_iteration_scratch_bytes(n, h, w)
+    scr = torch.empty(nscr, dtype=torch.uint8, device="cuda")
     rc = eng.lib.fdn_flow_iteration(dR[:n].data_ptr(), dR[n:].data_ptr(), dflow.data_ptr(), out.data_ptr(), n, h, w,
-                                    win, None)
+                                    win, scr.data_ptr(), nscr, None)
     assert rc == 0, eng.lib.fdn_last_error()
     got = out.cpu().numpy()
     for i in range(n):
         M = O.update_matrices(R[i], R[n + i], flow[i])
         ref = O.blur_solve(M, win)
         d = np.abs(got[i] - ref)
-        assert d.max() <= 1e-6, f"max|d|={d.max()}"
-        assert np.mean(got[i] == ref) >= 0.999, f"bit-equal fraction {np.mean(got[i] == ref)}"
+        assert np.array_equal(got[i], ref), f"max|d|={d.max()} bit-equal fraction {np.mean(got[i] == ref)}"
 
 
 def test_flow_resampling_bit_exact(eng):
@@ -184,13 +198,12 @@ def test_farneback_vs_reference_golden(eng, golden, case):
             got = flow[0].cpu().numpy()
             epe = np.sqrt(((got - ref) ** 2).sum(-1))
             print(f"case {case} chain{j}: EPE mean {epe.mean():.3e} max {epe.max():.3e} exact {np.mean(got == ref):.5f}")
-            assert epe.mean() <= 1e-6 and epe.max() <= 1e-3
-            assert np.mean(got == ref) >= 0.995
+            assert epe.mean() <= 0.05                      # north-star bound
+            assert np.array_equal(got, ref)                # what this implementation delivers
     f2 = torch.zeros_like(flow)
     eng.farneback(centre, dev(v[2:3]), f2, FlowParams(l, w, 3, 5, 1.2, False))
     ref = g[f"{case}_flow_noprev2"]
-    epe = np.sqrt(((f2[0].cpu().numpy() - ref) ** 2).sum(-1))
-    assert epe.mean() <= 1e-6 and epe.max() <= 1e-3
+    assert np.array_equal(f2[0].cpu().numpy(), ref)
 
 
 def test_farneback_vs_live_cv2(eng):
@@ -206,7 +219,7 @@ def test_farneback_vs_live_cv2(eng):
         epe = np.sqrt(((got - ref) ** 2).sum(-1))
         print(f"{shape} l{l} w{w}: EPE mean {epe.mean():.3e} max {epe.max():.3e} exact {np.mean(got == ref):.5f}")
         assert epe.mean() <= 0.05          # north-star bound
-        assert epe.mean() <= 1e-5 and epe.max() <= 1e-2   # what this implementation actually delivers
+        assert np.array_equal(got, ref)    # what this implementation actually delivers (AVX2 host, see oracle)
 
 
 def test_transpose(eng):
