@@ -21,6 +21,8 @@
 //   Every R0 / flow row is read once (no vertical halo), R1 gathers mostly hit L1/L2.
 //   Algorithmic HBM bytes per pixel: R0 20 + R1 20 + flow in 8 + flow out 8 = 56.
 // Compiled with -fmad=false: OpenCV's scalar code has no fused multiply-adds here.
+#include <stdlib.h>
+
 #include "fdn_internal.cuh"
 
 namespace fdn {
@@ -102,14 +104,25 @@ __device__ __forceinline__ void update_matrices_px(const float4* __restrict__ R0
     M[4] = __fadd_rn(__fmul_rn(r6, r2), __fmul_rn(r5, r3));
 }
 
-template <int CW, int TR>
-__global__ void __launch_bounds__(CW + 32)
+constexpr int tile_line_stride(int cw, int m)
+{
+    int ls = cw + 2 * m + 2;
+    while (ls % 16 != 1) ls++;
+    return ls;
+}
+
+// MT > 0: half window m = MT known at compile time (winsize 5 -> MT 2, winsize 9 -> MT 4): ring / tile strides fold
+// into immediates. MT == 0: generic m from the arguments.
+template <int CW, int TR, int MT, int MINB>
+__global__ void __launch_bounds__(CW + 32, MINB)
 k_flow_iter(FlowIterArgs a)
 {
     constexpr int NT = CW + 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int m = a.m, h = a.h, w = a.w, LS = a.LS;
+    const int m = MT > 0 ? MT : a.m;
+    const int LS = MT > 0 ? tile_line_stride(CW, MT) : a.LS;
     const int RR = 2 * m + 2;
+    const int h = a.h, w = a.w;
     double* tile = reinterpret_cast<double*>(smem_raw);                               // [TR*5][LS]
     float* ring = reinterpret_cast<float*>(smem_raw + sizeof(double) * TR * 5 * LS);  // [RR][5][NT]
 
@@ -147,8 +160,9 @@ k_flow_iter(FlowIterArgs a)
 
     double vs[5] = {0, 0, 0, 0, 0};
     int next_row = 0;       // next M row to compute
-    int next_slot = 0;      // its ring slot (= next_row mod RR)
-    int slot_old = 0;       // ring slot of row max(y-m-1, 0)
+    float* ring_new = ring + t;   // ring slot of next_row      (slot stride 5*NT, channel stride NT)
+    float* ring_old = ring + t;   // ring slot of row max(y-m-1, 0)
+    float* const ring_end = ring + RR * 5 * NT;
     float Mv[5];
 
     if (active) {
@@ -157,8 +171,9 @@ k_flow_iter(FlowIterArgs a)
         for (; next_row <= last_init; next_row++) {
             update_matrices_px(R0a, R0b, R1a, R1b, fin, xcl, next_row, h, w, Mv);
 #pragma unroll
-            for (int c = 0; c < 5; c++) ring[(next_slot * 5 + c) * NT + t] = Mv[c];
-            next_slot = next_slot + 1 == RR ? 0 : next_slot + 1;
+            for (int c = 0; c < 5; c++) ring_new[c * NT] = Mv[c];
+            ring_new += 5 * NT;
+            if (ring_new >= ring_end) ring_new -= RR * 5 * NT;
         }
         const float mp2 = (float)(m + 2);
 #pragma unroll
@@ -174,38 +189,39 @@ k_flow_iter(FlowIterArgs a)
     for (int y0 = 0; y0 < h; y0 += TR, tile_idx++) {
         // ---------------- phase V: column sums of TR rows ----------------
         if (active) {
+            double* tq = tile + q;
 #pragma unroll
             for (int r = 0; r < TR; r++) {
                 const int y = y0 + r;
                 if (y < h) {
-                    const int j1 = min(y + m, h - 1);
-                    int s1;
-                    if (next_row <= j1) {  // exactly one new row per step while y + m < h
+                    if (next_row <= min(y + m, h - 1)) {  // exactly one new row per step while y + m < h
                         update_matrices_px(R0a, R0b, R1a, R1b, fin, xcl, next_row, h, w, Mv);
 #pragma unroll
-                        for (int c = 0; c < 5; c++) ring[(next_slot * 5 + c) * NT + t] = Mv[c];
-                        s1 = next_slot;
-                        next_slot = next_slot + 1 == RR ? 0 : next_slot + 1;
+                        for (int c = 0; c < 5; c++) ring_new[c * NT] = Mv[c];
+                        ring_new += 5 * NT;
+                        if (ring_new >= ring_end) ring_new -= RR * 5 * NT;
                         next_row++;
                     } else {  // bottom border: row h-1 again (the last slot written)
-                        s1 = next_slot == 0 ? RR - 1 : next_slot - 1;
+                        const float* last = (ring_new == ring + t ? ring_end + t : ring_new) - 5 * NT;
 #pragma unroll
-                        for (int c = 0; c < 5; c++) Mv[c] = ring[(s1 * 5 + c) * NT + t];
+                        for (int c = 0; c < 5; c++) Mv[c] = last[c * NT];
                     }
-                    // row max(y-m-1, 0): slot_old advances once y-m-1 > 0
 #pragma unroll
                     for (int c = 0; c < 5; c++) {
-                        const float d = __fsub_rn(Mv[c], ring[(slot_old * 5 + c) * NT + t]);
+                        const float d = __fsub_rn(Mv[c], ring_old[c * NT]);
                         vs[c] = __dadd_rn(vs[c], (double)d);
-                        tile[(r * 5 + c) * LS + q] = vs[c];
+                        tq[(r * 5 + c) * LS] = vs[c];
                     }
-                    if (y >= m + 1) slot_old = slot_old + 1 == RR ? 0 : slot_old + 1;  // row max(y-m, 0) next
+                    if (y >= m + 1) {  // row max(y-m, 0) next
+                        ring_old += 5 * NT;
+                        if (ring_old >= ring_end) ring_old -= RR * 5 * NT;
+                    }
                 }
             }
         }
         if (t == 0 && k > 0) {  // the left strip must have published this tile's carries
             const unsigned long long want = a.epoch + (unsigned long long)tile_idx + 1ull;
-            while (*flag_in < want) __nanosleep(40);
+            while (*flag_in < want) __nanosleep(20);
             __threadfence();
         }
         __syncthreads();
@@ -223,11 +239,36 @@ k_flow_iter(FlowIterArgs a)
                 } else {
                     S = __ldcg(carry_in + (int64_t)y * 5 + c);
                 }
+                // S(i) = S(i-1) + (vs[i+m] - vs[i-m-1]); S(i) overwrites the dead slot of column i-m-1. The differences
+                // of the next batch are formed before this batch's stores, so only the add chain is serial.
                 const int off = 2 * m + 1;
-#pragma unroll 4
-                for (int i = 0; i < ncols; i++) {
-                    const double d = __dsub_rn(line[i + off], line[i]);
-                    S = __dadd_rn(S, d);
+                constexpr int HB = 8;
+                int i = 0;
+                if (ncols >= HB) {
+                    double d[HB];
+#pragma unroll
+                    for (int u = 0; u < HB; u++) d[u] = __dsub_rn(line[u + off], line[u]);
+                    for (; i + 2 * HB <= ncols; i += HB) {
+                        double d2[HB];
+#pragma unroll
+                        for (int u = 0; u < HB; u++) d2[u] = __dsub_rn(line[i + HB + u + off], line[i + HB + u]);
+#pragma unroll
+                        for (int u = 0; u < HB; u++) {
+                            S = __dadd_rn(S, d[u]);
+                            line[i + u] = S;
+                        }
+#pragma unroll
+                        for (int u = 0; u < HB; u++) d[u] = d2[u];
+                    }
+#pragma unroll
+                    for (int u = 0; u < HB; u++) {
+                        S = __dadd_rn(S, d[u]);
+                        line[i + u] = S;
+                    }
+                    i += HB;
+                }
+                for (; i < ncols; i++) {
+                    S = __dadd_rn(S, __dsub_rn(line[i + off], line[i]));
                     line[i] = S;
                 }
                 if (k + 1 < a.strips) {
@@ -240,13 +281,14 @@ k_flow_iter(FlowIterArgs a)
         if (t == 0 && k + 1 < a.strips) *flag_out = a.epoch + (unsigned long long)tile_idx + 1ull;
         // ---------------- phase S: solve ----------------
         if (core) {
+            const double* tt = tile + t;
 #pragma unroll
             for (int r = 0; r < TR; r++) {
                 const int y = y0 + r;
                 if (y < h) {
                     double g[5];
 #pragma unroll
-                    for (int c = 0; c < 5; c++) g[c] = __dmul_rn(tile[(r * 5 + c) * LS + t], a.scale);
+                    for (int c = 0; c < 5; c++) g[c] = __dmul_rn(tt[(r * 5 + c) * LS], a.scale);
                     const double det = __dadd_rn(__dsub_rn(__dmul_rn(g[0], g[2]), __dmul_rn(g[1], g[1])), 1e-3);
                     const double idet = __ddiv_rn(1., det);
                     float2 o;
@@ -261,16 +303,16 @@ k_flow_iter(FlowIterArgs a)
 }
 
 static unsigned long long g_flow_epoch = 1;
+#define FDN_MAX_STRIPS 64
 
 // Scratch layout: [flags: n * MAX_STRIPS u64][carries: n * strips * h * 5 f64]. The flag area has the same place
 // and size for every pyramid level that shares the scratch (it only ever holds epochs of earlier launches, which
 // compare below the current one); the carry area is rewritten by every launch before it is read.
-#define FDN_MAX_STRIPS 64
+static int strip_width(int w) { return w > 96 ? 128 : 32; }
 
 size_t flow_iter_scratch_bytes(int n, int h, int w)
 {
-    const int CW = w > 96 ? 128 : 32;
-    const size_t strips = (size_t)cdiv(w, CW);
+    const size_t strips = (size_t)cdiv(w, strip_width(w));
     const size_t carry = sizeof(double) * 5 * (size_t)n * strips * h;
     const size_t flags = sizeof(unsigned long long) * (size_t)n * FDN_MAX_STRIPS;
     return ((carry + 255) / 256) * 256 + ((flags + 255) / 256) * 256;
@@ -283,6 +325,19 @@ int flow_iter_scratch_init(void* scratch, size_t bytes, cudaStream_t st)
     return FDN_OK;
 }
 
+template <int CW, int TR, int MT, int MINB>
+static int launch_flow_variant(const FlowIterArgs& a, dim3 grid, size_t smem, cudaStream_t st)
+{
+    static bool attr_set = false;
+    if (!attr_set) {
+        FDN_CUDA(cudaFuncSetAttribute(k_flow_iter<CW, TR, MT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      200 * 1024));
+        attr_set = true;
+    }
+    k_flow_iter<CW, TR, MT, MINB><<<grid, CW + 32, smem, st>>>(a);
+    return FDN_OK;
+}
+
 int launch_flow_iter(const float* R, int64_t R_stride, SlotMap map0, SlotMap map1, const float* flow_in,
                      float* flow_out, int n, int h, int w, int winsize, void* scratch, size_t scratch_bytes,
                      cudaStream_t st)
@@ -291,31 +346,25 @@ int launch_flow_iter(const float* R, int64_t R_stride, SlotMap map0, SlotMap map
     FDN_CHECK_ARG(flow_in != flow_out, "flow_in and flow_out must not alias");
     FDN_CHECK_ARG((int64_t)h * w < (1ll << 28), "level image too large");
     FDN_CHECK_ARG(scratch && scratch_bytes >= flow_iter_scratch_bytes(n, h, w), "flow iteration scratch too small");
-    constexpr int TR = 4;
     FlowIterArgs a;
     a.R = R; a.R_stride = R_stride;
     a.h = h; a.w = w; a.m = winsize / 2;
     a.scale = 1. / ((double)winsize * winsize);
-    const int RR = 2 * a.m + 2;
+    const int m = a.m;
+    const int RR = 2 * m + 2;
     const bool wide = w > 96;
-    const int CW = wide ? 128 : 32;
+    const int CW = strip_width(w);
     const int NT = CW + 32;
+    // tile rows per step: 6 when the compile-time m = 2 kernel applies (ring rows = tile rows), else 4
+    const int TR = (wide && m == 2) ? 6 : 4;
     a.strips = (int)cdiv(w, CW);
-    int LS = CW + 2 * a.m + 2;
-    while (LS % 16 != 1) LS++;
-    a.LS = LS;
+    a.LS = tile_line_stride(CW, m);
     // flags first (fixed place and size), carries behind them; a smaller level fits into the level-0 scratch
     FDN_CHECK_ARG(a.strips <= FDN_MAX_STRIPS, "image too wide (%d strips)", a.strips);
     const size_t flag_bytes = ((sizeof(unsigned long long) * (size_t)n * FDN_MAX_STRIPS + 255) / 256) * 256;
     a.flags = static_cast<unsigned long long*>(scratch);
     a.carry = reinterpret_cast<double*>(static_cast<char*>(scratch) + flag_bytes);
-    const size_t smem = sizeof(double) * TR * 5 * LS + sizeof(float) * RR * 5 * NT;
-    static bool attr_set = false;
-    if (!attr_set) {
-        FDN_CUDA(cudaFuncSetAttribute(k_flow_iter<128, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        FDN_CUDA(cudaFuncSetAttribute(k_flow_iter<32, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
-    }
+    const size_t smem = sizeof(double) * TR * 5 * a.LS + sizeof(float) * RR * 5 * NT;
     const unsigned long long tiles = (unsigned long long)cdiv(h, TR);
     for (int b0 = 0; b0 < n; b0 += 65535) {
         const int nb = n - b0 < 65535 ? n - b0 : 65535;
@@ -326,8 +375,16 @@ int launch_flow_iter(const float* R, int64_t R_stride, SlotMap map0, SlotMap map
         a.epoch = g_flow_epoch;
         ProfScope ps(K_FLOW_ITER, 56.0 * nb * h * w, st);
         dim3 grid((unsigned)a.strips, (unsigned)nb);
-        if (wide) k_flow_iter<128, TR><<<grid, 160, smem, st>>>(a);
-        else k_flow_iter<32, TR><<<grid, 64, smem, st>>>(a);
+        int rc;
+        if (wide) {
+            if (m == 2) rc = launch_flow_variant<128, 6, 2, 4>(a, grid, smem, st);
+            else if (m == 4) rc = launch_flow_variant<128, 4, 4, 4>(a, grid, smem, st);
+            else rc = launch_flow_variant<128, 4, 0, 4>(a, grid, smem, st);
+        } else {
+            if (m == 2) rc = launch_flow_variant<32, 4, 2, 8>(a, grid, smem, st);
+            else rc = launch_flow_variant<32, 4, 0, 8>(a, grid, smem, st);
+        }
+        if (rc) return rc;
         FDN_LAUNCHED("k_flow_iter");
         a.carry += (int64_t)nb * a.strips * h * 5;
         a.flags += (int64_t)nb * a.strips;
