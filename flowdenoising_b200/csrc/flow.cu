@@ -44,11 +44,9 @@ struct FlowIterArgs {
 
 __device__ __forceinline__ void update_matrices_px(const float4* __restrict__ R0a, const float* __restrict__ R0b,
                                                    const float4* __restrict__ R1a, const float* __restrict__ R1b,
-                                                   const float2* __restrict__ flow, int x, int y, int h, int w,
-                                                   float M[5])
+                                                   const float2 f, int x, int y, int h, int w, float M[5])
 {
     const int idx = y * w + x;
-    const float2 f = __ldg(flow + idx);
     const float dx = f.x, dy = f.y;
     float fx = __fadd_rn((float)x, dx), fy = __fadd_rn((float)y, dy);
     const int x1 = (int)floorf(fx), y1 = (int)floorf(fy);
@@ -169,7 +167,7 @@ k_flow_iter(FlowIterArgs a)
         // rows 0 .. m-1 (clamped to h-1) seed the column sums: vsum = M[0]*(m+2) + sum_{y=1}^{m-1} M[min(y,h-1)]
         const int last_init = min(max(m - 1, 0), h - 1);
         for (; next_row <= last_init; next_row++) {
-            update_matrices_px(R0a, R0b, R1a, R1b, fin, xcl, next_row, h, w, Mv);
+            update_matrices_px(R0a, R0b, R1a, R1b, __ldg(fin + next_row * w + xcl), xcl, next_row, h, w, Mv);
 #pragma unroll
             for (int c = 0; c < 5; c++) ring_new[c * NT] = Mv[c];
             ring_new += 5 * NT;
@@ -185,6 +183,16 @@ k_flow_iter(FlowIterArgs a)
         }
     }
 
+    // Step y of the march consumes the new row y + m. The flow of a tile's TR new rows is fetched one tile ahead
+    // (issued before the block waits for the horizontal scan), so phase V exposes one memory latency per row (the R1
+    // gather) instead of two dependent ones.
+    float2 fl[TR];
+#pragma unroll
+    for (int r = 0; r < TR; r++) {
+        fl[r] = make_float2(0.f, 0.f);
+        if (active && r + m < h) fl[r] = __ldg(fin + (r + m) * w + xcl);
+    }
+
     int tile_idx = 0;
     for (int y0 = 0; y0 < h; y0 += TR, tile_idx++) {
         // ---------------- phase V: column sums of TR rows ----------------
@@ -195,7 +203,7 @@ k_flow_iter(FlowIterArgs a)
                 const int y = y0 + r;
                 if (y < h) {
                     if (next_row <= min(y + m, h - 1)) {  // exactly one new row per step while y + m < h
-                        update_matrices_px(R0a, R0b, R1a, R1b, fin, xcl, next_row, h, w, Mv);
+                        update_matrices_px(R0a, R0b, R1a, R1b, fl[r], xcl, next_row, h, w, Mv);  // next_row == y + m
 #pragma unroll
                         for (int c = 0; c < 5; c++) ring_new[c * NT] = Mv[c];
                         ring_new += 5 * NT;
@@ -225,6 +233,13 @@ k_flow_iter(FlowIterArgs a)
             __threadfence();
         }
         __syncthreads();
+        if (active) {  // flows of the next tile's new rows: in flight while the scan and the solve run
+#pragma unroll
+            for (int r = 0; r < TR; r++) {
+                const int row = y0 + TR + r + m;
+                if (row < h) fl[r] = __ldg(fin + row * w + xcl);
+            }
+        }
         // ---------------- phase H: sequential horizontal running sums ----------------
         if (t < 5 * TR) {
             const int r = t / 5, c = t - r * 5;

@@ -10,7 +10,6 @@ TIFFs (compressed, tiled) go through Pillow if it is importable. Output is float
 """
 from __future__ import annotations
 
-import mmap
 import os
 import struct
 import time
@@ -149,40 +148,37 @@ def _tiff_pages(buf, path):
 
 def read_tiff(path: str) -> np.ndarray:
     with open(path, "rb") as f:
-        try:
-            buf = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ)
-        except ValueError:
-            raise ValueError(f"{path}: empty file")
-        try:
-            bo, pages = _tiff_pages(buf, path)
-            out = []
-            for t in pages:
-                comp = t.get(259, (1,))[0]
-                spp = t.get(277, (1,))[0]
-                if comp != 1 or spp != 1 or 322 in t:
-                    raise NotImplementedError
-                w, h = t[256][0], t[257][0]
-                bits = t.get(258, (1,))[0]
-                fmt = t.get(339, (1,))[0]
-                kind = {1: "u", 2: "i", 3: "f"}.get(fmt)
-                if kind is None or bits not in (8, 16, 32, 64):
-                    raise NotImplementedError
-                dt = np.dtype(f"{bo}{kind}{bits // 8}")
-                offs, cnts = t[273], t[279]
-                if len(offs) == 1:
-                    page = np.frombuffer(buf, dtype=dt, count=w * h, offset=offs[0])
-                else:
-                    page = np.concatenate([np.frombuffer(buf, dtype=np.uint8, count=c, offset=o)
-                                           for o, c in zip(offs, cnts)]).view(dt)[:w * h]
-                out.append(page.reshape(h, w))
-            if not out:
-                raise ValueError(f"{path}: no images")
-            vol = np.stack(out) if len(out) > 1 else out[0][None]
-            return vol.astype(vol.dtype.newbyteorder("="))
-        except NotImplementedError:
-            pass
-        finally:
-            buf.close()
+        buf = f.read()
+    if len(buf) < 8:
+        raise ValueError(f"{path}: not a TIFF file")
+    try:
+        bo, pages = _tiff_pages(buf, path)
+        out = []
+        for t in pages:
+            comp = t.get(259, (1,))[0]
+            spp = t.get(277, (1,))[0]
+            if comp != 1 or spp != 1 or 322 in t:
+                raise NotImplementedError
+            w, h = t[256][0], t[257][0]
+            bits = t.get(258, (1,))[0]
+            fmt = t.get(339, (1,))[0]
+            kind = {1: "u", 2: "i", 3: "f"}.get(fmt)
+            if kind is None or bits not in (8, 16, 32, 64):
+                raise NotImplementedError
+            dt = np.dtype(f"{bo}{kind}{bits // 8}")
+            offs, cnts = t[273], t[279]
+            if len(offs) == 1:
+                page = np.frombuffer(buf, dtype=dt, count=w * h, offset=offs[0])
+            else:
+                page = np.concatenate([np.frombuffer(buf, dtype=np.uint8, count=c, offset=o)
+                                       for o, c in zip(offs, cnts)]).view(dt)[:w * h]
+            out.append(page.reshape(h, w))
+        if not out:
+            raise ValueError(f"{path}: no images")
+        vol = np.stack(out) if len(out) > 1 else out[0][None]
+        return vol.astype(vol.dtype.newbyteorder("="))
+    except NotImplementedError:
+        pass
     # compressed / tiled / palette TIFFs: Pillow
     from PIL import Image
     with Image.open(path) as im:
