@@ -316,8 +316,20 @@ def main():
     if dom:
         kd = kern[dom]
         achieved = kd["bytes"] / (kd["ms"] * 1e-3) / 1e9
+        # DRAM traffic per launch: ratio measured once with `ncu --set full` (profiles/r1_traffic.json) x the
+        # algorithmic bytes of this run's average launch; null if no capture is committed for the kernel
+        traffic, traffic_src = None, None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+                tr = json.load(f).get(dom)
+            if tr:
+                traffic = tr["dram_bytes_per_algorithmic_byte"] * kd["bytes"] / kd["launches"]
+                traffic_src = tr["source"]
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                    "peak_source": peak_src,
                     "avg_launch_ms": kd["ms"] / kd["launches"], "launches": kd["launches"],
                     "algorithmic_bytes_per_launch": kd["bytes"] / kd["launches"],
                     "share_of_step": kd["ms"] / (ms_total if ms_total > 0 else 1.0),
