@@ -6,7 +6,10 @@
 // fused, float32 vs float64) follows OpenCV so that results are bit-identical to the CPU reference on
 // AVX2 hosts; this file is compiled with -fmad=false and fuses only where fmaf() is written.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
+
+#include <cuda.h>
 
 #include "fdn_internal.cuh"
 
@@ -319,12 +322,199 @@ k_polyexp(const float* __restrict__ img, int64_t img_stride, float* __restrict__
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Stage 2 with TMA: the same arithmetic, input tiles brought in by the Tensor Memory Accelerator.
+// A block walks along one row of 32x32 output tiles; while it computes tile i, the (32+2n)^2 input box of tile
+// i+1 is already in flight (cp.async.bulk.tensor into the other shared-memory buffer, completion on an mbarrier).
+// TMA zero-fills out-of-image elements; the replicate border OpenCV uses is applied when the tile is read (clamped
+// tile coordinates -- the clamped source always lies inside the same box).
+// Needs w % 4 == 0 (16-byte global strides); other widths use k_polyexp.
+// ------------------------------------------------------------------------------------------------
+// TMA needs the box's innermost start coordinate 16-byte aligned (4 floats) [probe: unaligned starts fault]: the box
+// begins PL = 8 columns left of the tile (>= poly_n) instead of poly_n columns.
+#define PL 8
+#define PBX_MAX ((PL + PT + PN_MAX + 3) & ~3)
+#define PBY_MAX (PT + 2 * PN_MAX)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    }
+}
+
+// one thread arms the mbarrier with the byte count and starts the 3-D bulk tensor copy (box -> shared memory)
+__device__ __forceinline__ void tma_load_box(uint64_t tmap_addr, uint32_t dst, uint32_t bar, uint32_t bytes, int cx,
+                                             int cy, int cz)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        :: "r"(dst), "l"(tmap_addr), "r"(cx), "r"(cy), "r"(cz), "r"(bar) : "memory");
+}
+
+__global__ void __launch_bounds__(256)
+k_polyexp_tma(const __grid_constant__ CUtensorMap tmap, float* __restrict__ R, int64_t R_stride, SlotMap R_map, int h,
+              int w, PolyConsts pc)
+{
+    __shared__ __align__(128) float s_in[2][PBY_MAX * PBX_MAX];
+    __shared__ float s_row[3][PT][PT + 2 * PN_MAX + 1];
+    __shared__ __align__(8) unsigned long long s_bar[2];
+    const int n = pc.n;
+    const int TW = PT + 2 * n;           // columns / rows actually used
+    const int BX = (PL + PT + n + 3) & ~3;   // box width (multiple of 4 floats = 16 bytes), the tile's row pitch
+    const int y0 = blockIdx.y * PT, b = blockIdx.z;
+    const int ntiles = (w + PT - 1) / PT;
+    const uint32_t box_bytes = (uint32_t)(BX * TW * sizeof(float));
+    const uint32_t bar0 = smem_u32(&s_bar[0]), bar1 = smem_u32(&s_bar[1]);
+
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar0));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    // the descriptor must be addressed in the kernel-parameter (constant) space: take the address here, not through
+    // a by-reference capture (a local copy of the 128-byte map would make the bulk copy fault)
+    const uint64_t tmap_addr = reinterpret_cast<uint64_t>(&tmap);
+    const uint32_t dst0 = smem_u32(&s_in[0][0]), dst1 = smem_u32(&s_in[1][0]);
+    if (threadIdx.x == 0) tma_load_box(tmap_addr, dst0, bar0, box_bytes, -PL, y0 - n, b);
+
+    float* dstR = R + (int64_t)R_map.slot(b) * R_stride;
+    for (int tile = 0; tile < ntiles; tile++) {
+        const int buf = tile & 1;
+        if (threadIdx.x == 0 && tile + 1 < ntiles)   // prefetch the next tile into the other buffer
+            tma_load_box(tmap_addr, buf ? dst0 : dst1, buf ? bar0 : bar1, box_bytes, (tile + 1) * PT - PL, y0 - n, b);
+        mbar_wait(buf ? bar1 : bar0, (uint32_t)((tile >> 1) & 1));
+        const float* tin = s_in[buf];
+        const int x0 = tile * PT;
+        const int gx0 = x0 - PL, gy0 = y0 - n;   // global coordinates of the box origin
+        const bool border = x0 - n < 0 || gy0 < 0 || x0 + PT + n > w || gy0 + TW > h;
+        // vertical pass: PT rows x TW columns
+        for (int i = threadIdx.x; i < PT * TW; i += 256) {
+            const int ty = i / TW, tx = i - ty * TW;
+            float t0, t1 = 0.f, t2 = 0.f;
+            if (!border) {
+                const float* c = tin + (ty + n) * BX + tx + (PL - n);
+                t0 = __fmul_rn(c[0], pc.g[0]);
+                for (int k = 1; k <= n; k++) {
+                    const float a0 = c[-k * BX], a1 = c[k * BX];
+                    const float p = __fadd_rn(a0, a1);
+                    t0 = __fadd_rn(t0, __fmul_rn(pc.g[k], p));
+                    t1 = __fadd_rn(t1, __fmul_rn(pc.xg[k], __fsub_rn(a1, a0)));
+                    t2 = __fadd_rn(t2, __fmul_rn(pc.xxg[k], p));
+                }
+            } else {  // replicate: clamp the GLOBAL coordinate, then address the box
+                const int cx = min(max(x0 - n + tx, 0), w - 1) - gx0;
+                const int gy = gy0 + ty + n;
+                const float* col = tin + cx;
+                t0 = __fmul_rn(col[(min(max(gy, 0), h - 1) - gy0) * BX], pc.g[0]);
+                for (int k = 1; k <= n; k++) {
+                    const float a0 = col[(min(max(gy - k, 0), h - 1) - gy0) * BX];
+                    const float a1 = col[(min(max(gy + k, 0), h - 1) - gy0) * BX];
+                    const float p = __fadd_rn(a0, a1);
+                    t0 = __fadd_rn(t0, __fmul_rn(pc.g[k], p));
+                    t1 = __fadd_rn(t1, __fmul_rn(pc.xg[k], __fsub_rn(a1, a0)));
+                    t2 = __fadd_rn(t2, __fmul_rn(pc.xxg[k], p));
+                }
+            }
+            s_row[0][ty][tx] = t0; s_row[1][ty][tx] = t1; s_row[2][ty][tx] = t2;
+        }
+        __syncthreads();
+        // horizontal pass (identical to k_polyexp)
+        for (int i = threadIdx.x; i < PT * PT; i += 256) {
+            const int ty = i / PT, tx = i - ty * PT;
+            const int gy = y0 + ty, gx = x0 + tx;
+            if (gy >= h || gx >= w) continue;
+            const float* r0 = &s_row[0][ty][tx + n];
+            const float* r1 = &s_row[1][ty][tx + n];
+            const float* r2 = &s_row[2][ty][tx + n];
+            float g0 = pc.g[0];
+            double b1 = (double)__fmul_rn(r0[0], g0), b2 = 0, b3 = (double)__fmul_rn(r1[0], g0), b4 = 0,
+                   b5 = (double)__fmul_rn(r2[0], g0), b6 = 0;
+            for (int k = 1; k <= n; k++) {
+                const double tg = (double)__fadd_rn(r0[k], r0[-k]);
+                g0 = pc.g[k];
+                b1 = __dadd_rn(b1, __dmul_rn(tg, (double)g0));
+                b4 = __dadd_rn(b4, __dmul_rn(tg, (double)pc.xxg[k]));
+                b2 = __dadd_rn(b2, (double)__fmul_rn(__fsub_rn(r0[k], r0[-k]), pc.xg[k]));
+                b3 = __dadd_rn(b3, (double)__fmul_rn(__fadd_rn(r1[k], r1[-k]), g0));
+                b6 = __dadd_rn(b6, (double)__fmul_rn(__fsub_rn(r1[k], r1[-k]), pc.xg[k]));
+                b5 = __dadd_rn(b5, (double)__fmul_rn(__fadd_rn(r2[k], r2[-k]), g0));
+            }
+            float4 o;
+            o.x = (float)__dmul_rn(b3, pc.ig11);
+            o.y = (float)__dmul_rn(b2, pc.ig11);
+            o.z = (float)__dadd_rn(__dmul_rn(b1, pc.ig03), __dmul_rn(b5, pc.ig33));
+            o.w = (float)__dadd_rn(__dmul_rn(b1, pc.ig03), __dmul_rn(b4, pc.ig33));
+            reinterpret_cast<float4*>(dstR)[(int64_t)gy * w + gx] = o;
+            dstR[(int64_t)4 * h * w + (int64_t)gy * w + gx] = (float)__dmul_rn(b6, pc.ig55);
+        }
+        __syncthreads();   // s_row and s_in[buf] are free again (the copy issued two tiles later reuses s_in[buf])
+    }
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled get_encode_tiled()
+{
+    static PFN_encodeTiled fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    }
+    return fn;
+}
+
+static bool g_polyexp_use_tma = true;   // FDN_POLYEXP_TMA=0 disables (A/B timing, tests exercise both)
+
 int launch_polyexp(const float* img, int64_t img_stride, float* R, int64_t R_stride, SlotMap R_map, int n, int h,
                    int w, const PolyConsts& pc, cudaStream_t st)
 {
     if (pc.n < 1 || pc.n > PN_MAX) {
         set_error("poly_n %d unsupported (1..%d)", pc.n, PN_MAX);
         return FDN_ERR_INVALID;
+    }
+    static bool env_read = false;
+    if (!env_read) {
+        env_read = true;
+        const char* e = getenv("FDN_POLYEXP_TMA");
+        if (e && atoi(e) == 0) g_polyexp_use_tma = false;
+    }
+    PFN_encodeTiled enc = g_polyexp_use_tma ? get_encode_tiled() : nullptr;
+    const bool tma_ok = enc && w % 4 == 0 && img_stride == (int64_t)h * w && w >= 4 &&
+                        (reinterpret_cast<uintptr_t>(img) & 15) == 0 && n <= 65535 && cdiv(h, PT) <= 65535;
+    if (tma_ok) {
+        const int TW = PT + 2 * pc.n;
+        CUtensorMap tmap;
+        const cuuint64_t gdim[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+        const cuuint64_t gstr[2] = {(cuuint64_t)w * 4, (cuuint64_t)h * w * 4};
+        const cuuint32_t box[3] = {(cuuint32_t)((PL + PT + pc.n + 3) & ~3), (cuuint32_t)TW, 1};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(img), gdim, gstr, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr == CUDA_SUCCESS) {
+            dim3 grid(1, (unsigned)cdiv(h, PT), (unsigned)n);
+            ProfScope ps(K_POLYEXP, 24.0 * n * h * w, st);
+            k_polyexp_tma<<<grid, 256, 0, st>>>(tmap, R, R_stride, R_map, h, w, pc);
+            FDN_LAUNCHED("k_polyexp_tma");
+            return FDN_OK;
+        }
     }
     for (int b0 = 0; b0 < n; b0 += 65535) {
         int nb = n - b0 < 65535 ? n - b0 : 65535;
