@@ -42,9 +42,13 @@ struct FlowIterArgs {
     unsigned long long epoch;
 };
 
+// ROWCHK = false: the caller guarantees 5 <= y < h - 5, so the border weight reduces to the column factor `sx`
+// (= border[x] * border[w-1-x], the first product OpenCV forms; the two row factors are exactly 1).
+template <bool ROWCHK = true>
 __device__ __forceinline__ void update_matrices_px(const float4* __restrict__ R0a, const float* __restrict__ R0b,
                                                    const float4* __restrict__ R1a, const float* __restrict__ R1b,
-                                                   const float2 f, int x, int y, int h, int w, float M[5])
+                                                   const float2 f, int x, int y, int h, int w, float M[5],
+                                                   bool colb = false, float sx = 1.f)
 {
     const int idx = y * w + x;
     const float dx = f.x, dy = f.y;
@@ -85,15 +89,20 @@ __device__ __forceinline__ void update_matrices_px(const float4* __restrict__ R0
     r3 = __fmul_rn(__fsub_rn(c03.y, r3), 0.5f);
     r2 = __fadd_rn(r2, __fadd_rn(__fmul_rn(r4, dy), __fmul_rn(r6, dx)));
     r3 = __fadd_rn(r3, __fadd_rn(__fmul_rn(r6, dy), __fmul_rn(r5, dx)));
-    if ((unsigned)(x - 5) >= (unsigned)(w - 10) || (unsigned)(y - 5) >= (unsigned)(h - 10)) {
-        // border[5] = {0.14, 0.14, 0.4472, 0.4472, 0.4472}
-        float s = x < 5 ? (x < 2 ? 0.14f : 0.4472f) : 1.f;
-        const int xr = w - x - 1, yr = h - y - 1;
-        s = __fmul_rn(s, x >= w - 5 ? (xr < 2 ? 0.14f : 0.4472f) : 1.f);
-        s = __fmul_rn(s, y < 5 ? (y < 2 ? 0.14f : 0.4472f) : 1.f);
-        s = __fmul_rn(s, y >= h - 5 ? (yr < 2 ? 0.14f : 0.4472f) : 1.f);
-        r2 = __fmul_rn(r2, s); r3 = __fmul_rn(r3, s); r4 = __fmul_rn(r4, s);
-        r5 = __fmul_rn(r5, s); r6 = __fmul_rn(r6, s);
+    if (ROWCHK) {
+        if ((unsigned)(x - 5) >= (unsigned)(w - 10) || (unsigned)(y - 5) >= (unsigned)(h - 10)) {
+            // border[5] = {0.14, 0.14, 0.4472, 0.4472, 0.4472}
+            float s = x < 5 ? (x < 2 ? 0.14f : 0.4472f) : 1.f;
+            const int xr = w - x - 1, yr = h - y - 1;
+            s = __fmul_rn(s, x >= w - 5 ? (xr < 2 ? 0.14f : 0.4472f) : 1.f);
+            s = __fmul_rn(s, y < 5 ? (y < 2 ? 0.14f : 0.4472f) : 1.f);
+            s = __fmul_rn(s, y >= h - 5 ? (yr < 2 ? 0.14f : 0.4472f) : 1.f);
+            r2 = __fmul_rn(r2, s); r3 = __fmul_rn(r3, s); r4 = __fmul_rn(r4, s);
+            r5 = __fmul_rn(r5, s); r6 = __fmul_rn(r6, s);
+        }
+    } else if (colb) {
+        r2 = __fmul_rn(r2, sx); r3 = __fmul_rn(r3, sx); r4 = __fmul_rn(r4, sx);
+        r5 = __fmul_rn(r5, sx); r6 = __fmul_rn(r6, sx);
     }
     M[0] = __fadd_rn(__fmul_rn(r4, r4), __fmul_rn(r6, r6));
     M[1] = __fmul_rn(__fadd_rn(r4, r5), r6);
@@ -142,6 +151,10 @@ k_flow_iter(FlowIterArgs a)
     const int xcl = min(max(x0 - m - 1 + q, 0), w - 1);
     const bool core = (t < CW) && (x0 + t < w);
     const int ncols = min(CW, w - x0);
+    // column part of the border weight (steady tiles): (x < 5 ? border[x] : 1) * (x >= w-5 ? border[w-1-x] : 1)
+    const bool colb = (unsigned)(xcl - 5) >= (unsigned)(w - 10);
+    const float sxc = __fmul_rn(xcl < 5 ? (xcl < 2 ? 0.14f : 0.4472f) : 1.f,
+                                xcl >= w - 5 ? (w - xcl - 1 < 2 ? 0.14f : 0.4472f) : 1.f);
 
     const float* R0 = a.R + (int64_t)a.map0.slot(b) * a.R_stride;
     const float* R1 = a.R + (int64_t)a.map1.slot(b) * a.R_stride;
@@ -196,7 +209,30 @@ k_flow_iter(FlowIterArgs a)
     int tile_idx = 0;
     for (int y0 = 0; y0 < h; y0 += TR, tile_idx++) {
         // ---------------- phase V: column sums of TR rows ----------------
-        if (active) {
+        // Steady tiles (every step brings a new row, no top/bottom border involved): with TR == ring rows the ring
+        // slots of a tile are compile-time constants -- row r is written to slot (m + r) % RR and the row leaving
+        // the window sits in slot (m + 1 + r) % RR -- and all bookkeeping branches disappear.
+        constexpr bool kStatic = MT > 0 && TR == 2 * MT + 2;
+        const bool steady = kStatic && y0 >= TR && y0 + TR - 1 + m <= h - 1 && y0 + m >= 5 && y0 + TR - 1 + m < h - 5;
+        if (active && steady) {
+            if constexpr (kStatic) {
+                constexpr int RRs = 2 * MT + 2;
+                double* tq = tile + q;
+                float* rg = ring + t;
+#pragma unroll
+                for (int r = 0; r < TR; r++) {
+                    update_matrices_px<false>(R0a, R0b, R1a, R1b, fl[r], xcl, y0 + r + MT, h, w, Mv, colb, sxc);
+#pragma unroll
+                    for (int c = 0; c < 5; c++) {
+                        rg[(((MT + r) % RRs) * 5 + c) * NT] = Mv[c];
+                        const float d = __fsub_rn(Mv[c], rg[(((MT + 1 + r) % RRs) * 5 + c) * NT]);
+                        vs[c] = __dadd_rn(vs[c], (double)d);
+                        tq[(r * 5 + c) * LS] = vs[c];
+                    }
+                }
+                next_row += TR;   // ring_new / ring_old come back to the same slots after TR == RR advances
+            }
+        } else if (active) {
             double* tq = tile + q;
 #pragma unroll
             for (int r = 0; r < TR; r++) {
@@ -305,7 +341,7 @@ k_flow_iter(FlowIterArgs a)
 #pragma unroll
                     for (int c = 0; c < 5; c++) g[c] = __dmul_rn(tt[(r * 5 + c) * LS], a.scale);
                     const double det = __dadd_rn(__dsub_rn(__dmul_rn(g[0], g[2]), __dmul_rn(g[1], g[1])), 1e-3);
-                    const double idet = __ddiv_rn(1., det);
+                    const double idet = __drcp_rn(det);  // == 1./det correctly rounded, like the IEEE division
                     float2 o;
                     o.x = (float)__dmul_rn(__dsub_rn(__dmul_rn(g[0], g[4]), __dmul_rn(g[1], g[3])), idet);
                     o.y = (float)__dmul_rn(__dsub_rn(__dmul_rn(g[2], g[3]), __dmul_rn(g[1], g[4])), idet);
