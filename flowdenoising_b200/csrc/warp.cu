@@ -54,9 +54,83 @@ k_warp_acc(const float* __restrict__ neigh, int64_t n_ss, int64_t n_rs, SlotMap 
     *ap = first ? (float)prod : (float)__dadd_rn((double)*ap, prod);
 }
 
+// Four consecutive pixels per thread (128-bit flow / accumulator accesses, four independent gathers in flight).
+// Same arithmetic as k_warp_acc. Needs W % 4 == 0 and 16-byte aligned rows.
+__device__ __forceinline__ float remap_px(const float* __restrict__ src, int64_t n_rs, float fx, float fy, int x, int y,
+                                          int H, int W)
+{
+    const float mx = __fadd_rn(fx, (float)x), my = __fadd_rn(fy, (float)y);
+    const int sx = __float2int_rn(__fmul_rn(mx, 32.f)), sy = __float2int_rn(__fmul_rn(my, 32.f));
+    const int ax = sx & 31, ay = sy & 31;
+    int ix = sx >> 5, iy = sy >> 5;
+    ix = min(max(ix, -32768), 32767);
+    iy = min(max(iy, -32768), 32767);
+    const float tx1 = __fmul_rn((float)ax, 0.03125f), tx0 = __fsub_rn(1.f, tx1);
+    const float ty1 = __fmul_rn((float)ay, 0.03125f), ty0 = __fsub_rn(1.f, ty1);
+    const float w0 = __fmul_rn(ty0, tx0), w1 = __fmul_rn(ty0, tx1), w2 = __fmul_rn(ty1, tx0), w3 = __fmul_rn(ty1, tx1);
+    const int x0 = min(max(ix, 0), W - 1), x1 = min(max(ix + 1, 0), W - 1);
+    const int y0 = min(max(iy, 0), H - 1), y1 = min(max(iy + 1, 0), H - 1);
+    const float* r0 = src + (int64_t)y0 * n_rs;
+    const float* r1 = src + (int64_t)y1 * n_rs;
+    const float v0 = __ldg(r0 + x0), v1 = __ldg(r0 + x1), v2 = __ldg(r1 + x0), v3 = __ldg(r1 + x1);
+    return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(v0, w0), __fmul_rn(v1, w1)), __fmul_rn(v2, w2)), __fmul_rn(v3, w3));
+}
+
+__global__ void __launch_bounds__(128)
+k_warp_acc4(const float* __restrict__ neigh, int64_t n_ss, int64_t n_rs, SlotMap n_map, const float4* __restrict__ flow,
+            double weight, float* __restrict__ acc, int64_t a_ss, int64_t a_rs, int H, int W, int first)
+{
+    const int x = (blockIdx.x * 128 + threadIdx.x) * 4;
+    const int y = blockIdx.y;
+    const int b = blockIdx.z;
+    if (x >= W) return;
+    const float* src = neigh + (int64_t)n_map.slot(b) * n_ss;
+    float v[4];
+    if (flow) {
+        const float4* fp = flow + (((int64_t)b * H + y) * W + x) / 2;   // two float2 flows per float4
+        const float4 f01 = __ldg(fp), f23 = __ldg(fp + 1);
+        v[0] = remap_px(src, n_rs, f01.x, f01.y, x, y, H, W);
+        v[1] = remap_px(src, n_rs, f01.z, f01.w, x + 1, y, H, W);
+        v[2] = remap_px(src, n_rs, f23.x, f23.y, x + 2, y, H, W);
+        v[3] = remap_px(src, n_rs, f23.z, f23.w, x + 3, y, H, W);
+    } else {
+        const float4 c = __ldg(reinterpret_cast<const float4*>(src + (int64_t)y * n_rs + x));
+        v[0] = c.x; v[1] = c.y; v[2] = c.z; v[3] = c.w;
+    }
+    float4* ap = reinterpret_cast<float4*>(acc + (int64_t)b * a_ss + (int64_t)y * a_rs + x);
+    float o[4];
+    if (first) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) o[i] = (float)__dmul_rn((double)v[i], weight);
+    } else {
+        const float4 a = *ap;
+        const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+        for (int i = 0; i < 4; i++) o[i] = (float)__dadd_rn((double)av[i], __dmul_rn((double)v[i], weight));
+    }
+    *ap = make_float4(o[0], o[1], o[2], o[3]);
+}
+
 int launch_warp_acc(const float* neigh, int64_t n_ss, int64_t n_rs, SlotMap n_map, const float* flow, double weight,
                     float* acc, int64_t a_ss, int64_t a_rs, int n, int H, int W, int first, cudaStream_t st)
 {
+    const bool vec4 = W % 4 == 0 && n_ss % 4 == 0 && n_rs % 4 == 0 && a_ss % 4 == 0 && a_rs % 4 == 0 &&
+                      (reinterpret_cast<uintptr_t>(neigh) & 15) == 0 && (reinterpret_cast<uintptr_t>(acc) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(flow) & 15) == 0;
+    if (vec4) {
+        for (int b0 = 0; b0 < n; b0 += 65535) {
+            const int nb = n - b0 < 65535 ? n - b0 : 65535;
+            SlotMap m = n_map;
+            m.base += b0;
+            dim3 grid((unsigned)cdiv(W, 512), (unsigned)H, (unsigned)nb);
+            ProfScope ps(K_WARP_ACC, (double)nb * H * W * (4.0 + (flow ? 8.0 : 0.0) + (first ? 4.0 : 8.0)), st);
+            k_warp_acc4<<<grid, 128, 0, st>>>(neigh, n_ss, n_rs, m,
+                                              flow ? reinterpret_cast<const float4*>(flow + (int64_t)b0 * H * W * 2) : nullptr,
+                                              weight, acc + (int64_t)b0 * a_ss, a_ss, a_rs, H, W, first);
+            FDN_LAUNCHED("k_warp_acc4");
+        }
+        return FDN_OK;
+    }
     for (int b0 = 0; b0 < n; b0 += 65535) {
         const int nb = n - b0 < 65535 ? n - b0 : 65535;
         SlotMap m = n_map;

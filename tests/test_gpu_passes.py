@@ -191,3 +191,20 @@ def test_module_surface_drop_in(golden):
     assert np.array_equal(w, f["a_warp_chain3"])
     with pytest.raises(AssertionError):
         obj.filter_along_Z(np.ones(4) / 4)      # even kernel: same assert as the reference (:309)
+
+
+@pytest.mark.parametrize("shape,sigmas,lw", [((7, 45, 67), (0.5, 1.0, 0.5), (3, 5)), ((9, 70, 53), (1.0, 0.5, 0.5), (2, 7))])
+def test_of_odd_shapes_vs_c_oracle(eng, shape, sigmas, lw):
+    """Odd sizes (non-power-of-two pyramid levels, partial strips/tiles, scalar tails of the blur): every pass equals
+    the C oracle (itself bit-exact vs cv2) bit for bit."""
+    from flowdenoising_b200.engine import FlowParams
+    vol = O.synthetic_volume(shape, seed=61, noise_sigma=8.0)
+    p = FlowParams(lw[0], lw[1])
+    cur = vol
+    for axis in range(3):
+        k = O.get_gaussian_kernel(sigmas[axis])
+        out = torch.empty_like(dev(cur))
+        eng.filter_along_axis(dev(cur), out, axis, k, p)
+        ref = O.flow_axis_c(cur, axis, k, levels=lw[0], winsize=lw[1])
+        check_of(f"odd {shape} axis {axis}", out.cpu().numpy(), ref)
+        cur = ref
