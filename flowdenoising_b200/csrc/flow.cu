@@ -405,11 +405,10 @@ struct WinCfg {
     static constexpr int HALO = 2 * MT + 1;
     static constexpr int CWMAX = (NT - HALO) & ~3;
     static constexpr int HY = 2;
-    static constexpr int C0 = MT - HY;                        // first R1 row of box 0
-    static constexpr int NEED = (TR + 2 * HY + 1 + SR - 1) / SR;   // boxes a tile reads
-    static constexpr int NBOX = NEED + 1;                     // + one in flight
-    static constexpr int NR = NBOX * SR;                      // ring rows
-    static constexpr int WROWS = NEED * SR;                   // rows readable during a tile
+    static constexpr int WROWS = TR + 2 * HY + 1;             // R1 rows a tile reads (around its vertical centre)
+    static constexpr int NR = WROWS + TR + 1;                 // ring rows: a tile's rows + the next tile's new rows
+                                                              // (the centre moves by at most one row per tile)
+    static constexpr int NBAR = 3;                            // mbarriers: one per tile, reused every 3 tiles
     static constexpr int XL = ((MT + 1 + 4) + 3) & ~3;        // window starts XL columns left of x0 (multiple of 4)
     static constexpr int WW = (XL - (MT + 1) + NT + 4 + 3) & ~3;   // window width (multiple of 4)
     static constexpr int LS = NT + 1;                         // tile line stride in doubles (== 1 mod 16)
@@ -419,7 +418,7 @@ struct WinCfg {
     static constexpr size_t ringB_off = ringA_off + ringA_bytes;
     static constexpr size_t ringB_bytes = (size_t)NR * WW * 4;
     static constexpr size_t bar_off = (ringB_off + ringB_bytes + 7) / 8 * 8;
-    static constexpr size_t smem_bytes = bar_off + 8 * NBOX;
+    static constexpr size_t smem_bytes = bar_off + 8 * NBAR + 16 + 16 * 4;   // + centres + partial sums
     static_assert(5 * TR <= 32, "phase H runs in one warp");
 };
 
@@ -553,8 +552,8 @@ __device__ __noinline__ M5 win_matrices_px_slow(RowIn in, WinState ws, int x, in
                                                 bool second_half)
 {
     M5 out;
-    if (second_half) win_matrices_px<C, C::WROWS, false>(in, ws, x, y, h, w, colb, sxc, out.v);
-    else win_matrices_px<C, C::WROWS - C::SR, false>(in, ws, x, y, h, w, colb, sxc, out.v);
+    (void)second_half;
+    win_matrices_px<C, C::WROWS, false>(in, ws, x, y, h, w, colb, sxc, out.v);
     return out;
 }
 
@@ -574,41 +573,55 @@ struct WinArgs {
     int exp;               // timing experiments (FDN_EXP), results are wrong when != 0
     unsigned tag;          // launch tag of the carry packets (never 0)
     ulonglong2* packets;   // [n][strips][h][5]: {lo32 | tag << 32, hi32 | tag << 32}
-    int2* centres;         // [n]: displacement the R1 window of a pair is centred on (x a multiple of 4)
+    int2* centres;         // [n][strips]: displacement the R1 window of a strip is centred on (x a multiple of 4)
 };
 
-// Where to centre the R1 window of each pair: the mean of a 32 x 32 sample grid of the incoming flow (neighbour
-// slices of a volume mostly differ by a drift; chained flows of distant neighbours carry several pixels of it).
-// The centre only decides which R1 rows / columns are staged in shared memory -- never a value -- so it may be
-// approximate (and its x component is rounded to a multiple of 4 for the 16-byte alignment of the bulk copies).
+// Where to centre the R1 window of each (pair, strip): the mean of a 16 x 64 sample grid of the incoming flow inside
+// the strip (neighbour slices of a volume mostly differ by a drift; chained flows of distant neighbours carry several
+// pixels of it). The centre only decides which R1 rows / columns are staged in shared memory -- never a value -- so
+// it may be approximate (its x component is rounded to a multiple of 4 for the 16-byte alignment of the bulk
+// copies; the y component is only the starting point, k_flow_iter_win then follows the flow tile by tile).
 __global__ void __launch_bounds__(256)
-k_flow_centre(const float2* __restrict__ flow, int h, int w, int2* __restrict__ centres)
+k_flow_centre(const float2* __restrict__ flow, int h, int w, int CW, int2* __restrict__ centres)
 {
-    const int b = blockIdx.x;
+    const int k = blockIdx.x, b = blockIdx.y;
+    const int x0 = k * CW, ncols = min(CW, w - x0);
     const float2* f = flow + (int64_t)b * h * w;
-    float sx = 0.f, sy = 0.f;
+    float sx = 0.f, sy = 0.f, sy0 = 0.f;
     for (int i = threadIdx.x; i < 1024; i += 256) {
-        const int gy = i >> 5, gx = i & 31;
-        const int y = (int)(((int64_t)(2 * gy + 1) * h) >> 6), x = (int)(((int64_t)(2 * gx + 1) * w) >> 6);
+        const int gy = i >> 4, gx = i & 15;
+        const int y = (int)(((int64_t)(2 * gy + 1) * h) >> 7), x = x0 + (((2 * gx + 1) * ncols) >> 5);
         const float2 v = __ldg(f + (int64_t)y * w + x);
-        if (fabsf(v.x) < 1e6f && fabsf(v.y) < 1e6f) { sx += v.x; sy += v.y; }   // NaN / Inf / wild samples: ignored
+        if (fabsf(v.x) < 1e6f && fabsf(v.y) < 1e6f) {   // NaN / Inf / wild samples: ignored
+            sx += v.x;
+            sy += v.y;
+        }
     }
-    __shared__ float red[2][8];
+    // the vertical centre is only the start of the march: the first rows of the strip
+    if (threadIdx.x < 64) {
+        const int gy = threadIdx.x >> 4, gx = threadIdx.x & 15;
+        const int y = min(2 * gy + 1, h - 1), x = x0 + (((2 * gx + 1) * ncols) >> 5);
+        const float2 v = __ldg(f + (int64_t)y * w + x);
+        if (fabsf(v.y) < 1e6f) sy0 = v.y;
+    }
+    __shared__ float red[3][8];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         sx += __shfl_xor_sync(0xffffffffu, sx, o);
         sy += __shfl_xor_sync(0xffffffffu, sy, o);
+        sy0 += __shfl_xor_sync(0xffffffffu, sy0, o);
     }
-    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = sx; red[1][threadIdx.x >> 5] = sy; }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = sx; red[1][threadIdx.x >> 5] = sy; red[2][threadIdx.x >> 5] = sy0; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        float tx = 0.f, ty = 0.f;
-        for (int i = 0; i < 8; i++) { tx += red[0][i]; ty += red[1][i]; }
-        tx *= (1.f / 1024.f); ty *= (1.f / 1024.f);
+        float tx = 0.f, ty0 = red[2][0] + red[2][1];
+        for (int i = 0; i < 8; i++) tx += red[0][i];
+        tx *= (1.f / 1024.f);
+        ty0 *= (1.f / 64.f);
         int2 c;
         c.x = (int)rintf(fminf(fmaxf(tx, (float)-w), (float)w) * 0.25f) * 4;
-        c.y = (int)rintf(fminf(fmaxf(ty, (float)-h), (float)h));
-        centres[b] = c;
+        c.y = (int)rintf(fminf(fmaxf(ty0, (float)-h), (float)h));
+        centres[(int64_t)b * gridDim.x + k] = c;
     }
 }
 
@@ -657,7 +670,7 @@ k_flow_iter_win(WinArgs wa)
     const uint32_t bar0 = smem_addr(bars);
     if (t == 0) {
 #pragma unroll
-        for (int i = 0; i < C::NBOX; i++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar0 + 8 * i));
+        for (int i = 0; i < C::NBAR; i++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar0 + 8 * i));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -760,36 +773,48 @@ k_flow_iter_win(WinArgs wa)
     ws.R1b = R1 + (int64_t)4 * h * w;
     ws.ringA = ringA;
     ws.ringB = ringB;
-    const int2 centre = wa.centres[b];
+    // Window geometry. Horizontally the window is centred on the strip's mean flow (centre.x, constant). Vertically
+    // it follows the flow: tile j reads R1 rows [A_j, A_j + WROWS), A_j = TR*j + m - HY + c_j, where the centre c_j
+    // is the rounded mean vertical flow of the tile's own rows (known one tile ahead: the rows are prefetched),
+    // limited to a change of one row per tile so that the ring (row y lives in ring row y mod NR) only ever grows
+    // at its lower end: the rows [B_{j+1}, B_{j+2}) are fetched after phase V of tile j, one mbarrier per tile.
+    const int2 centre = wa.centres[(int64_t)b * a.strips + k];
+    int* s_c = reinterpret_cast<int*>(smem_raw + C::bar_off + 8 * C::NBAR);        // [3] centres c_j by j % 3
+    float* s_part = reinterpret_cast<float*>(smem_raw + C::bar_off + 8 * C::NBAR + 16);   // [NT / 32] partial sums
     ws.xs = x0 - C::XL + centre.x;
-    ws.ybase = C::C0 + centre.y;
-    ws.rb = 0;
+    ws.ybase = m - C::HY + centre.y;
+    ws.rb = ((ws.ybase % C::NR) + C::NR) % C::NR;
 
-    // box B = R1 rows [SR*B + C0 + centre.y, +SR) x window columns, clipped to the image, into ring rows (SR*B) % NR ...
+    // fetch R1 rows [lo, hi) x window columns (clipped to the image) into the ring; completion on mbarrier `slot`
     const int cx0 = max(ws.xs, 0), cx1 = min(ws.xs + C::WW, w);
-    auto issue_box = [&](int B) {
-        const int slot = B % C::NBOX;
+    auto issue_rows = [&](int lo, int hi, int slot) {
         const uint32_t bar = bar0 + 8 * slot;
-        const int ya = SR * B + C::C0 + centre.y;
-        const int lo = max(ya, 0), hi = min(ya + SR, h);   // valid rows [lo, hi)
+        const int vlo = max(lo, 0), vhi = min(hi, h);
         const int cols = cx1 - cx0;
-        if (hi <= lo || cols <= 0) {
+        if (vhi <= vlo || cols <= 0) {
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
             return;
         }
-        const uint32_t bytes = (uint32_t)((hi - lo) * cols * 20);
+        const uint32_t bytes = (uint32_t)((vhi - vlo) * cols * 20);
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
-        for (int yy = lo; yy < hi; yy++) {
-            const int rr = slot * SR + (yy - ya);
+        int rr = vlo % C::NR;   // vlo >= 0
+        for (int yy = vlo; yy < vhi; yy++) {
             const int so = rr * C::WW + (cx0 - ws.xs);
             bulk_g2s(smem_addr(ringA + so), ws.R1a + ((int64_t)yy * w + cx0), (uint32_t)cols * 16, bar);
             bulk_g2s(smem_addr(ringB + so), ws.R1b + ((int64_t)yy * w + cx0), (uint32_t)cols * 4, bar);
+            rr = rr + 1 == C::NR ? 0 : rr + 1;
         }
     };
-    auto wait_box = [&](int B) { mbar_wait_parity(bar0 + 8 * (B % C::NBOX), (uint32_t)((B / C::NBOX) & 1)); };
+    auto wait_tile = [&](int j) { mbar_wait_parity(bar0 + 8 * (j % C::NBAR), (uint32_t)((j / C::NBAR) & 1)); };
+    // the issuing thread's bookkeeping: fetched up to row `fetched` (exclusive), centre of the last tile planned
+    int fetched = 0, c_last = centre.y;
     if (t == NT - 1) {
-#pragma unroll
-        for (int B = 0; B < C::NBOX; B++) issue_box(B);
+        const int A0 = m - C::HY + centre.y;
+        issue_rows(A0, A0 + C::WROWS, 0);                       // tile 0
+        issue_rows(A0 + C::WROWS, A0 + C::WROWS + TR, 1);       // tile 1, same centre
+        fetched = A0 + C::WROWS + TR;
+        s_c[0] = centre.y;
+        s_c[1] = centre.y;
     }
 
     auto load_row = [&](int y) {
@@ -816,9 +841,7 @@ k_flow_iter_win(WinArgs wa)
 #pragma unroll
         for (int c = 0; c < 5; c++) Mring[s][c] = 0.f;
 
-    // tile 0 reads boxes 0 .. NEED-1; the last one is awaited in the middle of its phase V
-#pragma unroll
-    for (int B = 0; B < C::NEED - 1; B++) wait_box(B);
+    wait_tile(0);   // the rows of tile 0 also serve the seed rows below (where they do not, the global gather does)
 
     if (active) {
         // rows 0 .. m-1 seed the column sums: vsum = M[0]*(m+2) + sum_{y=1}^{m-1} M[min(y,h-1)]
@@ -878,44 +901,53 @@ k_flow_iter_win(WinArgs wa)
     auto tile_step = [&](int j, RowIn (&cur)[TR]) {
         const int y0 = j * TR;
         double* tq = tiles + (j & 1) * TR * 5 * LS + t;
-        // tile j reads boxes 2j .. 2j+NEED-1; all but the last two were awaited by the tile before
-        if (j > 0) wait_box(2 * j + C::NEED - 2);
+        if (j > 0) {
+            wait_tile(j);
+            const int cj = s_c[j % C::NBAR];
+            ws.ybase = y0 + m - C::HY + cj;
+            ws.rb = ((ws.ybase % C::NR) + C::NR) % C::NR;
+        }
 #pragma unroll
         for (int half = 0; half < 2; half++) {
-            if (half == 1) wait_box(2 * j + C::NEED - 1);   // rows of the second half reach into the newest box
+            // The SR rows of a half are independent up to the column sums: one straight-line block (the compiler
+            // interleaves the rows) that gathers from the window. Pixels whose taps leave the window (sparse: flow
+            // outliers) are then redone, lane by lane, by the out-of-line function with the global gather.
             // (threads beyond the halo carry zero flows: they never ask for the global gather)
-            bool slow = false;
+            bool miss[SR];
+            bool anymiss = false;
 #pragma unroll
             for (int rr = 0; rr < SR; rr++) {
                 const int r = half * SR + rr;
                 const int yn = min(y0 + r + m, h - 1);
-                if (half == 0) slow |= win_needs_global<C, C::WROWS - C::SR>(cur[r], ws, xcl, yn, h, w);
-                else slow |= win_needs_global<C, C::WROWS>(cur[r], ws, xcl, yn, h, w);
+                miss[rr] = active && win_needs_global<C, C::WROWS>(cur[r], ws, xcl, yn, h, w);
+                anymiss |= miss[rr];
             }
-            slow = __any_sync(0xffffffffu, slow && active);
-            if ((wa.exp & 64) && (t & 31) == 0) {
-                atomicAdd(&g_win_dbg[0], 1ull);
-                if (slow) atomicAdd(&g_win_dbg[1], 1ull);
-            }
-            // the SR rows of a half are independent up to the column sums: one straight-line block (the compiler
-            // interleaves the rows), the rare global-gather case goes through the out-of-line function
-            float Mv[SR][5];
-            if (!slow) {
-#pragma unroll
-                for (int rr = 0; rr < SR; rr++) {
-                    const int r = half * SR + rr;
-                    const int yn = min(y0 + r + m, h - 1);
-                    if (half == 0) win_matrices_px<C, C::WROWS - C::SR, true>(cur[r], ws, xcl, yn, h, w, colb, sxc, Mv[rr]);
-                    else win_matrices_px<C, C::WROWS, true>(cur[r], ws, xcl, yn, h, w, colb, sxc, Mv[rr]);
+            anymiss = __any_sync(0xffffffffu, anymiss);
+            if (wa.exp & 64) {
+                const unsigned bm = __ballot_sync(0xffffffffu, miss[0] || miss[1] || miss[2]);
+                if ((t & 31) == 0) {
+                    atomicAdd(&g_win_dbg[0], 1ull);
+                    if (anymiss) atomicAdd(&g_win_dbg[1], 1ull);
+                    atomicAdd(&g_win_dbg[2], (unsigned long long)__popc(bm));
                 }
-            } else {
+            }
+            float Mv[SR][5];
+#pragma unroll
+            for (int rr = 0; rr < SR; rr++) {
+                const int r = half * SR + rr;
+                const int yn = min(y0 + r + m, h - 1);
+                win_matrices_px<C, C::WROWS, true>(cur[r], ws, xcl, yn, h, w, colb, sxc, Mv[rr]);
+            }
+            if (anymiss) {
 #pragma unroll
                 for (int rr = 0; rr < SR; rr++) {
-                    const int r = half * SR + rr;
-                    const int yn = min(y0 + r + m, h - 1);
-                    const M5 ms = win_matrices_px_slow<C>(cur[r], ws, xcl, yn, h, w, colb, sxc, half == 1);
+                    if (miss[rr]) {
+                        const int r = half * SR + rr;
+                        const int yn = min(y0 + r + m, h - 1);
+                        const M5 ms = win_matrices_px_slow<C>(cur[r], ws, xcl, yn, h, w, colb, sxc, half == 1);
 #pragma unroll
-                    for (int c = 0; c < 5; c++) Mv[rr][c] = ms.v[c];
+                        for (int c = 0; c < 5; c++) Mv[rr][c] = ms.v[c];
+                    }
                 }
             }
             if (!(wa.exp & 4)) {
@@ -944,15 +976,33 @@ k_flow_iter_win(WinArgs wa)
             nbar_sync(BAR_DONE + ((j - 1) & 1), NT + 32);  // scan of tile j-1 finished
             phase_s(j - 1);
         }
-        // every column warp is past phase V of tile j (boxes 2j, 2j+1 are no longer read) and past phase S of tile
-        // j-1 (whose shared-memory tile phase V of tile j+1 overwrites)
+        // mean vertical flow of the NEXT tile's rows (in `cur` by now): where the tile after it centres its window
+        {
+            float sy = 0.f;
+            if (active) {
+#pragma unroll
+                for (int r = 0; r < TR; r++) sy += cur[r].f.y;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sy += __shfl_xor_sync(0xffffffffu, sy, o);
+            if ((t & 31) == 0) s_part[(j & 1) * (NT / 32) + (t >> 5)] = sy;
+        }
+        // every column warp is past phase V of tile j (its window rows above A_{j+1} are no longer read) and past
+        // phase S of tile j-1 (whose shared-memory tile phase V of tile j+1 overwrites)
         nbar_sync(BAR_COLS, NT);
         if (t == NT - 1) {
-            issue_box(2 * j + C::NBOX);
-            issue_box(2 * j + C::NBOX + 1);
+            float sy = 0.f;
+#pragma unroll
+            for (int i = 0; i < NT / 32; i++) sy += s_part[(j & 1) * (NT / 32) + i];
+            sy = sy / (float)((ncols + C::HALO) * TR);
+            int c = fabsf(sy) < 1e6f ? (int)rintf(sy) : c_last;
+            c = min(max(c, c_last - 1), c_last + 1);
+            c_last = c;
+            const int Bnext = (j + 2) * TR + m - C::HY + c + C::WROWS;   // B_{j+2}
+            issue_rows(fetched, Bnext, (j + 2) % C::NBAR);
+            fetched = max(fetched, Bnext);
+            s_c[(j + 2) % C::NBAR] = c;
         }
-        ws.ybase += TR;
-        ws.rb = ws.rb + TR >= C::NR ? ws.rb + TR - C::NR : ws.rb + TR;
     };
 
     for (int j = 0; j < ntiles; j++) tile_step(j, pfa);
@@ -979,7 +1029,7 @@ typedef WinCfg<2, FDN_WIN_NT> WinCfg2;
 
 static size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 static size_t flow_flag_bytes(int n) { return align256(sizeof(unsigned long long) * (size_t)n * FDN_MAX_STRIPS); }
-static size_t flow_offset_bytes(int n) { return align256(sizeof(int2) * (size_t)n); }   // window centres, one per pair
+static size_t flow_offset_bytes(int n) { return align256(sizeof(int2) * (size_t)n * FDN_MAX_STRIPS); }   // window centres
 static size_t flow_carry_bytes(int n, int h, int w)   // k_flow_iter: one double per (pair, strip, row, channel)
 {
     return align256(sizeof(double) * 5 * (size_t)n * (size_t)cdiv(w, strip_width(w)) * h);
@@ -990,7 +1040,7 @@ static size_t flow_packet_bytes(int n, int h, int w)  // k_flow_iter_win: one 16
     return align256(sizeof(ulonglong2) * 5 * (size_t)n * strips * h);
 }
 
-// Scratch layout: [flags: n * MAX_STRIPS u64][window centres: n int2][packets of k_flow_iter_win ...  ... carries of
+// Scratch layout: [flags: n * MAX_STRIPS u64][window centres: n * MAX_STRIPS int2][packets of k_flow_iter_win ...  ... carries of
 // k_flow_iter]. The flag
 // area has the same place and size for every pyramid level that shares the scratch (it only ever holds epochs of
 // earlier launches, which compare below the current one). Packets grow from the front and plain carries sit at the
@@ -1079,14 +1129,6 @@ int launch_flow_iter(const float* R, int64_t R_stride, SlotMap map0, SlotMap map
         if ((unsigned)g_flow_epoch == 0) g_flow_epoch++;   // the packet tag is the low word of the epoch, never 0
         wa.tag = (unsigned)g_flow_epoch;
         { const char* e = getenv("FDN_EXP"); wa.exp = e ? atoi(e) : 0; }
-        if (wa.exp & 64) {
-            unsigned long long c[4];
-            cudaMemcpyFromSymbol(c, g_win_dbg, sizeof c);
-            fprintf(stderr, "[fdn] before this launch (h=%d w=%d n=%d): warp-halves %llu, slow %llu (%.2f%%)\n", h, w, n, c[0],
-                    c[1], c[0] ? 100.0 * c[1] / c[0] : 0.0);
-            unsigned long long z[4] = {0, 0, 0, 0};
-            cudaMemcpyToSymbol(g_win_dbg, z, sizeof z);
-        }
         for (int b0 = 0; b0 < n; b0 += 65535) {
             const int nb = n - b0 < 65535 ? n - b0 : 65535;
             a.map0 = map0; a.map0.base += b0;
@@ -1096,15 +1138,25 @@ int launch_flow_iter(const float* R, int64_t R_stride, SlotMap map0, SlotMap map
             a.epoch = g_flow_epoch;
             wa.a = a;
             ProfScope ps(K_FLOW_ITER, 56.0 * nb * h * w, st);
-            k_flow_centre<<<nb, 256, 0, st>>>(reinterpret_cast<const float2*>(a.flow_in), h, w, wa.centres);
+            k_flow_centre<<<dim3((unsigned)a.strips, (unsigned)nb), 256, 0, st>>>(reinterpret_cast<const float2*>(a.flow_in), h, w,
+                                                                                 wa.CW, wa.centres);
             FDN_LAUNCHED("k_flow_centre");
             dim3 grid((unsigned)a.strips, (unsigned)nb);
             k_flow_iter_win<2, FDN_WIN_NT, 2><<<grid, FDN_WIN_NT + 128, WinCfg2::smem_bytes, st>>>(wa);
             FDN_LAUNCHED("k_flow_iter_win");
             wa.packets += (int64_t)nb * a.strips * h * 5;
-            wa.centres += nb;
+            wa.centres += (int64_t)nb * a.strips;
         }
         g_flow_epoch += tiles + 1;
+        if (wa.exp & 64) {
+            unsigned long long c[4];
+            cudaStreamSynchronize(st);
+            cudaMemcpyFromSymbol(c, g_win_dbg, sizeof c);
+            fprintf(stderr, "[fdn] win h=%d w=%d n=%d: warp-halves %llu, with misses %llu (%.2f%%), missing lanes %llu\n", h, w, n,
+                    c[0], c[1], c[0] ? 100.0 * c[1] / c[0] : 0.0, c[2]);
+            unsigned long long z[4] = {0, 0, 0, 0};
+            cudaMemcpyToSymbol(g_win_dbg, z, sizeof z);
+        }
         return FDN_OK;
     }
     for (int b0 = 0; b0 < n; b0 += 65535) {
