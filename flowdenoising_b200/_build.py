@@ -47,7 +47,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
     for s in SOURCES:
         o = os.path.join(HERE, "build", s.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-Xptxas", "-v", "-c", os.path.join(CSRC, s), "-o", o]
+        extra = os.environ.get("FDN_NVCC_EXTRA", "").split()   # experiments only (e.g. -DFDN_WS_PF=6)
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-Xptxas", "-v", "-c", os.path.join(CSRC, s), "-o", o]
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(o)
     log = []

@@ -356,41 +356,24 @@ k_flow_iter(FlowIterArgs a)
 
 
 // ------------------------------------------------------------------------------------------------
-// k_flow_iter_win: the same march, rebuilt around a shared-memory WINDOW of the R1 image (the gather target).
-//   * NT threads = one strip of CW <= NT - (2m+1) core columns plus its (m+1 | m) halo columns: no idle warp;
+// k_flow_iter_ws: the same march as k_flow_iter, rebuilt as a warp-specialised pipeline (default for winsize 5).
+//   * 256 threads = two warpgroups. The "column" warpgroup (128 threads: one strip of CW <= 120 core columns plus
+//     its (m+1 | m) halo columns, thread t <-> image column x0 - m - 1 + t) runs phases V and S; one warp of the
+//     "scan" warpgroup runs phase H. The column sums of a tile go into one of TWO shared-memory tiles, so the scan of
+//     tile j overlaps phase V of tile j+1 and phase S of tile j-1. Registers are moved between the warpgroups with
+//     setmaxnreg (168 per column thread, 88 per scan thread, 2 blocks per SM);
 //   * the ring of the last 2m+2 rows of M lives in REGISTERS: a tile is one ring period (TR = 2m+2 rows), so every
 //     ring slot is a compile-time constant of the unrolled row loop;
-//   * the R1 rows a tile can touch (flow displacements in [-HY, HY+1) x about [-5, 6)) are brought in by the
-//     bulk-copy engine (cp.async.bulk global -> shared, completion on an mbarrier) ahead of use, as boxes of m+1
-//     rows in a ring of NBOX boxes; the bilinear gather reads shared memory. Displacements that leave the window
-//     (or touch rows the ring does not hold) fall back to the global gather of k_flow_iter -- same arithmetic,
-//     same bits;
-//   * R0 and the flow of the next tile's rows are register-prefetched before the block waits for the scan;
+//   * phase V is branch-free (selects, clamped gather addresses): the m+1 rows of half a tile form one straight-line
+//     block whose dependency chains the compiler interleaves. The bilinear gather reads R1 through L1 -- the
+//     kernel's shared memory is small (62 KB per block), so about 100 KB of L1 remain per SM and the rows of R1 a strip
+//     walks over stay resident; R0 / flow rows are streamed (evict-first) and register-prefetched one tile ahead;
 //   * carries between strips travel as self-validating packets {32 data bits, 32-bit launch tag} (two per double,
 //     one 16-byte store): no fences, no flag, only the 5*TR scanning lanes ever wait for the left strip;
-//   * phase H keeps two chunks of differences in flight, so its critical path is the dependent DADD alone.
-// Phase S is that of k_flow_iter. Needs w % 4 == 0 (16-byte aligned rows of the 1-channel plane).
+//   * phase H keeps the differences of the next 8 columns in registers, so its serial part is the dependent DADD;
+//   * phase S runs a full tile as one straight-line block.
+// Same arithmetic, same order of operations, same bits as k_flow_iter. Needs w % 4 == 0.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_wait_parity(uint32_t bar, uint32_t parity)
-{
-    uint32_t done = 0;
-    while (!done) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    }
-}
-
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-
 struct RowIn {
     float2 f;
     float4 c03;
@@ -398,46 +381,24 @@ struct RowIn {
 };
 
 template <int MT, int NT_>
-struct WinCfg {
+struct WsCfg {
     static constexpr int NT = NT_;
     static constexpr int TR = 2 * MT + 2;   // tile rows = ring period
-    static constexpr int SR = MT + 1;       // rows per box
+    static constexpr int SR = MT + 1;       // rows per straight-line block
     static constexpr int HALO = 2 * MT + 1;
     static constexpr int CWMAX = (NT - HALO) & ~3;
-    static constexpr int HY = 2;
-    static constexpr int WROWS = TR + 2 * HY + 1;             // R1 rows a tile reads (around its vertical centre)
-    static constexpr int NR = WROWS + TR + 1;                 // ring rows: a tile's rows + the next tile's new rows
-                                                              // (the centre moves by at most one row per tile)
-    static constexpr int NBAR = 3;                            // mbarriers: one per tile, reused every 3 tiles
-    static constexpr int XL = ((MT + 1 + 4) + 3) & ~3;        // window starts XL columns left of x0 (multiple of 4)
-    static constexpr int WW = (XL - (MT + 1) + NT + 4 + 3) & ~3;   // window width (multiple of 4)
-    static constexpr int LS = NT + 1;                         // tile line stride in doubles (== 1 mod 16)
-    static constexpr size_t tile_bytes = 2 * sizeof(double) * TR * 5 * LS;   // two tiles
-    static constexpr size_t ringA_off = (tile_bytes + 127) / 128 * 128;
-    static constexpr size_t ringA_bytes = (size_t)NR * WW * 16;
-    static constexpr size_t ringB_off = ringA_off + ringA_bytes;
-    static constexpr size_t ringB_bytes = (size_t)NR * WW * 4;
-    static constexpr size_t bar_off = (ringB_off + ringB_bytes + 7) / 8 * 8;
-    static constexpr size_t smem_bytes = bar_off + 8 * NBAR + 16 + 16 * 4;   // + centres + partial sums
+    static constexpr int LS = NT + 1;       // tile line stride in doubles (== 1 mod 16)
+    static constexpr size_t smem_bytes = 2 * sizeof(double) * TR * 5 * LS;   // two tiles
+    static_assert(LS % 16 == 1, "tile line stride must be 1 mod 16 doubles");
     static_assert(5 * TR <= 32, "phase H runs in one warp");
 };
 
-struct WinState {
-    const float4* R1a;
-    const float* R1b;
-    const float4* ringA;
-    const float* ringB;
-    int xs;      // image column of window column 0
-    int ybase;   // image row of the first readable ring row
-    int rb;      // its ring row index
-};
-
-// ROWS = ring rows (counted from ws.ybase) that have landed when this pixel is computed.
-// FAST = the caller has checked (for the whole warp) that no pixel needs the global-memory gather: straight-line
-// code (selects instead of branches), so that the compiler can interleave the rows of a tile.
-template <class C, int ROWS, bool FAST>
-__device__ __forceinline__ void win_matrices_px(const RowIn& in, const WinState& ws, int x, int y, int h, int w,
-                                                bool colb, float sxc, float M[5])
+// M of one pixel, branch-free: the bilinear taps are read at clamped (always valid) positions and discarded by a
+// select when the displaced position lies outside the image, exactly as the branch of update_matrices_px would.
+template <int PF>
+__device__ __forceinline__ void ws_matrices_px(const RowIn& in, const float4* __restrict__ R1a,
+                                               const float* __restrict__ R1b, int x, int y, int h, int w, float sxc,
+                                               float M[5])
 {
     const float dx = in.f.x, dy = in.f.y;
     float fx = __fadd_rn((float)x, dx), fy = __fadd_rn((float)y, dy);
@@ -446,95 +407,46 @@ __device__ __forceinline__ void win_matrices_px(const RowIn& in, const WinState&
     fy = __fsub_rn(fy, (float)y1);
     const float4 c03 = in.c03;
     const float c4 = in.c4;
-    float r2, r3, r4, r5, r6;
     const bool in_img = (unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1);
-    const int wx = x1 - ws.xs, ry = y1 - ws.ybase;
+    const int yc = min(max(y1, 0), h - 2), xc = min(max(x1, 0), w - 2);
+    const int g = yc * w + xc;
+    if (PF > 0) {
+        // warm L1 with the R1 rows this column will gather from PF rows further down (the flow is smooth)
+        const int gp = min(yc + PF + 1, h - 1) * w + xc;
+        asm volatile("prefetch.global.L1 [%0];" :: "l"(R1a + gp));
+        asm volatile("prefetch.global.L1 [%0];" :: "l"(R1b + gp));
+    }
+    const float4 p00 = __ldg(R1a + g), p01 = __ldg(R1a + g + 1), p10 = __ldg(R1a + g + w), p11 = __ldg(R1a + g + w + 1);
+    const float q00 = __ldg(R1b + g), q01 = __ldg(R1b + g + 1), q10 = __ldg(R1b + g + w), q11 = __ldg(R1b + g + w + 1);
+    const float ofx = __fsub_rn(1.f, fx), ofy = __fsub_rn(1.f, fy);
+    const float a00 = __fmul_rn(ofx, ofy), a01 = __fmul_rn(fx, ofy), a10 = __fmul_rn(ofx, fy), a11 = __fmul_rn(fx, fy);
 #define FDN_BILIN(v00, v01, v10, v11) \
     __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a00, v00), __fmul_rn(a01, v01)), __fmul_rn(a10, v10)), __fmul_rn(a11, v11))
-    if (FAST) {
-        // out-of-image pixels read a clamped (valid, meaningless) window position and discard the result
-        const int wxc = min(max(wx, 0), C::WW - 2), ryc = min(max(ry, 0), ROWS - 2);
-        int r0 = ws.rb + ryc;
-        r0 = r0 >= C::NR ? r0 - C::NR : r0;
-        int r1 = r0 + 1;
-        r1 = r1 >= C::NR ? 0 : r1;
-        const int i0 = r0 * C::WW + wxc, i1 = r1 * C::WW + wxc;
-        const float4 p00 = ws.ringA[i0], p01 = ws.ringA[i0 + 1], p10 = ws.ringA[i1], p11 = ws.ringA[i1 + 1];
-        const float q00 = ws.ringB[i0], q01 = ws.ringB[i0 + 1], q10 = ws.ringB[i1], q11 = ws.ringB[i1 + 1];
-        const float ofx = __fsub_rn(1.f, fx), ofy = __fsub_rn(1.f, fy);
-        const float a00 = __fmul_rn(ofx, ofy), a01 = __fmul_rn(fx, ofy), a10 = __fmul_rn(ofx, fy),
-                    a11 = __fmul_rn(fx, fy);
-        r2 = FDN_BILIN(p00.x, p01.x, p10.x, p11.x);
-        r3 = FDN_BILIN(p00.y, p01.y, p10.y, p11.y);
-        r4 = FDN_BILIN(p00.z, p01.z, p10.z, p11.z);
-        r5 = FDN_BILIN(p00.w, p01.w, p10.w, p11.w);
-        r6 = FDN_BILIN(q00, q01, q10, q11);
-        r4 = __fmul_rn(__fadd_rn(c03.z, r4), 0.5f);
-        r5 = __fmul_rn(__fadd_rn(c03.w, r5), 0.5f);
-        r6 = __fmul_rn(__fadd_rn(c4, r6), 0.25f);
-        r2 = in_img ? r2 : 0.f;
-        r3 = in_img ? r3 : 0.f;
-        r4 = in_img ? r4 : c03.z;
-        r5 = in_img ? r5 : c03.w;
-        r6 = in_img ? r6 : __fmul_rn(c4, 0.5f);
-    } else if (in_img) {
-        const float ofx = __fsub_rn(1.f, fx), ofy = __fsub_rn(1.f, fy);
-        const float a00 = __fmul_rn(ofx, ofy), a01 = __fmul_rn(fx, ofy), a10 = __fmul_rn(ofx, fy),
-                    a11 = __fmul_rn(fx, fy);
-        float4 p00, p01, p10, p11;
-        float q00, q01, q10, q11;
-        if ((unsigned)wx <= (unsigned)(C::WW - 2) && (unsigned)ry <= (unsigned)(ROWS - 2)) {
-            int r0 = ws.rb + ry;
-            r0 = r0 >= C::NR ? r0 - C::NR : r0;
-            int r1 = r0 + 1;
-            r1 = r1 >= C::NR ? 0 : r1;
-            const int i0 = r0 * C::WW + wx, i1 = r1 * C::WW + wx;
-            p00 = ws.ringA[i0]; p01 = ws.ringA[i0 + 1]; p10 = ws.ringA[i1]; p11 = ws.ringA[i1 + 1];
-            q00 = ws.ringB[i0]; q01 = ws.ringB[i0 + 1]; q10 = ws.ringB[i1]; q11 = ws.ringB[i1 + 1];
-        } else {
-            const int g = y1 * w + x1;
-            p00 = __ldg(ws.R1a + g); p01 = __ldg(ws.R1a + g + 1); p10 = __ldg(ws.R1a + g + w);
-            p11 = __ldg(ws.R1a + g + w + 1);
-            q00 = __ldg(ws.R1b + g); q01 = __ldg(ws.R1b + g + 1); q10 = __ldg(ws.R1b + g + w);
-            q11 = __ldg(ws.R1b + g + w + 1);
-        }
-        r2 = FDN_BILIN(p00.x, p01.x, p10.x, p11.x);
-        r3 = FDN_BILIN(p00.y, p01.y, p10.y, p11.y);
-        r4 = FDN_BILIN(p00.z, p01.z, p10.z, p11.z);
-        r5 = FDN_BILIN(p00.w, p01.w, p10.w, p11.w);
-        r6 = FDN_BILIN(q00, q01, q10, q11);
-        r4 = __fmul_rn(__fadd_rn(c03.z, r4), 0.5f);
-        r5 = __fmul_rn(__fadd_rn(c03.w, r5), 0.5f);
-        r6 = __fmul_rn(__fadd_rn(c4, r6), 0.25f);
-    } else {
-        r2 = r3 = 0.f;
-        r4 = c03.z;
-        r5 = c03.w;
-        r6 = __fmul_rn(c4, 0.5f);
-    }
+    float r2 = FDN_BILIN(p00.x, p01.x, p10.x, p11.x);
+    float r3 = FDN_BILIN(p00.y, p01.y, p10.y, p11.y);
+    float r4 = FDN_BILIN(p00.z, p01.z, p10.z, p11.z);
+    float r5 = FDN_BILIN(p00.w, p01.w, p10.w, p11.w);
+    float r6 = FDN_BILIN(q00, q01, q10, q11);
 #undef FDN_BILIN
+    r4 = __fmul_rn(__fadd_rn(c03.z, r4), 0.5f);
+    r5 = __fmul_rn(__fadd_rn(c03.w, r5), 0.5f);
+    r6 = __fmul_rn(__fadd_rn(c4, r6), 0.25f);
+    r2 = in_img ? r2 : 0.f;
+    r3 = in_img ? r3 : 0.f;
+    r4 = in_img ? r4 : c03.z;
+    r5 = in_img ? r5 : c03.w;
+    r6 = in_img ? r6 : __fmul_rn(c4, 0.5f);
     r2 = __fmul_rn(__fsub_rn(c03.x, r2), 0.5f);
     r3 = __fmul_rn(__fsub_rn(c03.y, r3), 0.5f);
     r2 = __fadd_rn(r2, __fadd_rn(__fmul_rn(r4, dy), __fmul_rn(r6, dx)));
     r3 = __fadd_rn(r3, __fadd_rn(__fmul_rn(r6, dy), __fmul_rn(r5, dx)));
-    if (FAST) {
-        // ((border_x_left * border_x_right) * border_y_top) * border_y_bottom; all factors are 1 away from the
-        // borders and x * 1.f == x bit for bit, so the product is applied unconditionally
-        float s = sxc;
-        s = __fmul_rn(s, y < 5 ? (y < 2 ? 0.14f : 0.4472f) : 1.f);
-        s = __fmul_rn(s, y >= h - 5 ? (h - y - 1 < 2 ? 0.14f : 0.4472f) : 1.f);
-        r2 = __fmul_rn(r2, s); r3 = __fmul_rn(r3, s); r4 = __fmul_rn(r4, s);
-        r5 = __fmul_rn(r5, s); r6 = __fmul_rn(r6, s);
-    } else {
-        const bool rowb = (unsigned)(y - 5) >= (unsigned)(h - 10);
-        if (colb || rowb) {
-            float s = sxc;
-            s = __fmul_rn(s, y < 5 ? (y < 2 ? 0.14f : 0.4472f) : 1.f);
-            s = __fmul_rn(s, y >= h - 5 ? (h - y - 1 < 2 ? 0.14f : 0.4472f) : 1.f);
-            r2 = __fmul_rn(r2, s); r3 = __fmul_rn(r3, s); r4 = __fmul_rn(r4, s);
-            r5 = __fmul_rn(r5, s); r6 = __fmul_rn(r6, s);
-        }
-    }
+    // border weight ((border_x_left * border_x_right) * border_y_top) * border_y_bottom; every factor is 1 away from
+    // the borders and x * 1.f == x bit for bit, so the product is applied unconditionally
+    float s = sxc;
+    s = __fmul_rn(s, y < 5 ? (y < 2 ? 0.14f : 0.4472f) : 1.f);
+    s = __fmul_rn(s, y >= h - 5 ? (h - y - 1 < 2 ? 0.14f : 0.4472f) : 1.f);
+    r2 = __fmul_rn(r2, s); r3 = __fmul_rn(r3, s); r4 = __fmul_rn(r4, s);
+    r5 = __fmul_rn(r5, s); r6 = __fmul_rn(r6, s);
     M[0] = __fadd_rn(__fmul_rn(r4, r4), __fmul_rn(r6, r6));
     M[1] = __fmul_rn(__fadd_rn(r4, r5), r6);
     M[2] = __fadd_rn(__fmul_rn(r5, r5), __fmul_rn(r6, r6));
@@ -542,90 +454,17 @@ __device__ __forceinline__ void win_matrices_px(const RowIn& in, const WinState&
     M[4] = __fadd_rn(__fmul_rn(r6, r2), __fmul_rn(r5, r3));
 }
 
-// Out-of-line copy of the general (branching, global-gather capable) pixel function: the rare path of phase V is
-// kept out of the unrolled row loop so that the hot loop stays small (instruction cache).
-struct M5 {
-    float v[5];
-};
-template <class C>
-__device__ __noinline__ M5 win_matrices_px_slow(RowIn in, WinState ws, int x, int y, int h, int w, bool colb, float sxc,
-                                                bool second_half)
-{
-    M5 out;
-    (void)second_half;
-    win_matrices_px<C, C::WROWS, false>(in, ws, x, y, h, w, colb, sxc, out.v);
-    return out;
-}
+#ifndef FDN_WS_PF
+#define FDN_WS_PF 6
+#endif
 
-// true when the pixel's bilinear taps lie inside the image but outside the ROWS x WW window (needs the global gather)
-template <class C, int ROWS>
-__device__ __forceinline__ bool win_needs_global(const RowIn& in, const WinState& ws, int x, int y, int h, int w)
-{
-    const int x1 = (int)floorf(__fadd_rn((float)x, in.f.x)), y1 = (int)floorf(__fadd_rn((float)y, in.f.y));
-    const bool in_img = (unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1);
-    const bool in_win = (unsigned)(x1 - ws.xs) <= (unsigned)(C::WW - 2) && (unsigned)(y1 - ws.ybase) <= (unsigned)(ROWS - 2);
-    return in_img && !in_win;
-}
-
-struct WinArgs {
+struct WsArgs {
     FlowIterArgs a;
     int CW;
     int exp;               // timing experiments (FDN_EXP), results are wrong when != 0
     unsigned tag;          // launch tag of the carry packets (never 0)
     ulonglong2* packets;   // [n][strips][h][5]: {lo32 | tag << 32, hi32 | tag << 32}
-    int2* centres;         // [n][strips]: displacement the R1 window of a strip is centred on (x a multiple of 4)
 };
-
-// Where to centre the R1 window of each (pair, strip): the mean of a 16 x 64 sample grid of the incoming flow inside
-// the strip (neighbour slices of a volume mostly differ by a drift; chained flows of distant neighbours carry several
-// pixels of it). The centre only decides which R1 rows / columns are staged in shared memory -- never a value -- so
-// it may be approximate (its x component is rounded to a multiple of 4 for the 16-byte alignment of the bulk
-// copies; the y component is only the starting point, k_flow_iter_win then follows the flow tile by tile).
-__global__ void __launch_bounds__(256)
-k_flow_centre(const float2* __restrict__ flow, int h, int w, int CW, int2* __restrict__ centres)
-{
-    const int k = blockIdx.x, b = blockIdx.y;
-    const int x0 = k * CW, ncols = min(CW, w - x0);
-    const float2* f = flow + (int64_t)b * h * w;
-    float sx = 0.f, sy = 0.f, sy0 = 0.f;
-    for (int i = threadIdx.x; i < 1024; i += 256) {
-        const int gy = i >> 4, gx = i & 15;
-        const int y = (int)(((int64_t)(2 * gy + 1) * h) >> 7), x = x0 + (((2 * gx + 1) * ncols) >> 5);
-        const float2 v = __ldg(f + (int64_t)y * w + x);
-        if (fabsf(v.x) < 1e6f && fabsf(v.y) < 1e6f) {   // NaN / Inf / wild samples: ignored
-            sx += v.x;
-            sy += v.y;
-        }
-    }
-    // the vertical centre is only the start of the march: the first rows of the strip
-    if (threadIdx.x < 64) {
-        const int gy = threadIdx.x >> 4, gx = threadIdx.x & 15;
-        const int y = min(2 * gy + 1, h - 1), x = x0 + (((2 * gx + 1) * ncols) >> 5);
-        const float2 v = __ldg(f + (int64_t)y * w + x);
-        if (fabsf(v.y) < 1e6f) sy0 = v.y;
-    }
-    __shared__ float red[3][8];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        sx += __shfl_xor_sync(0xffffffffu, sx, o);
-        sy += __shfl_xor_sync(0xffffffffu, sy, o);
-        sy0 += __shfl_xor_sync(0xffffffffu, sy0, o);
-    }
-    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = sx; red[1][threadIdx.x >> 5] = sy; red[2][threadIdx.x >> 5] = sy0; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float tx = 0.f, ty0 = red[2][0] + red[2][1];
-        for (int i = 0; i < 8; i++) tx += red[0][i];
-        tx *= (1.f / 1024.f);
-        ty0 *= (1.f / 64.f);
-        int2 c;
-        c.x = (int)rintf(fminf(fmaxf(tx, (float)-w), (float)w) * 0.25f) * 4;
-        c.y = (int)rintf(fminf(fmaxf(ty0, (float)-h), (float)h));
-        centres[(int64_t)b * gridDim.x + k] = c;
-    }
-}
-
-__device__ unsigned long long g_win_dbg[4];   // FDN_EXP & 64: [0] warp-halves, [1] of them on the slow path
 
 // named barriers (id 0 is __syncthreads)
 __device__ __forceinline__ void nbar_sync(int id, int count)
@@ -637,27 +476,21 @@ __device__ __forceinline__ void nbar_arrive(int id, int count)
     asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(count) : "memory");
 }
 
-// Warp roles: warps 0 .. NT/32-1 (the "column warps", thread t <-> tile position t) run phases V and S; one more warp
-// (the "scan warp") runs phase H. The column sums of a tile go into one of TWO shared-memory tiles, so the scan of
-// tile j overlaps phase V of tile j+1:
+// Roles and hand-offs:
 //   column warps:  V(j) -> arrive FULL[j&1] -> wait DONE[(j-1)&1] -> S(j-1) -> barrier among column warps -> V(j+1) ...
 //   scan warp:     wait FULL[j&1] -> H(j) in place -> arrive DONE[j&1] -> ...
 // Registers: the kernel is compiled for (65536 / 2 blocks / 256 threads) = 128 per thread; the column warpgroup then
-// takes 168 (setmaxnreg.inc) and the scan warpgroup keeps 88 (setmaxnreg.dec) -- 2 blocks per SM.
-template <int MT, int NT_, int MINB>
-__global__ void __launch_bounds__(NT_ + 128, MINB)
-k_flow_iter_win(WinArgs wa)
+// takes 168 (setmaxnreg.inc) and the scan warpgroup keeps 88 (setmaxnreg.dec).
+template <int MT, int NT_>
+__global__ void __launch_bounds__(NT_ + 128, 2)
+k_flow_iter_ws(WsArgs wa)
 {
-    using C = WinCfg<MT, NT_>;
+    using C = WsCfg<MT, NT_>;
     constexpr int NT = C::NT, TR = C::TR, SR = C::SR, RR = C::TR, LS = C::LS, m = MT;
     constexpr int BAR_FULL = 1, BAR_DONE = 3, BAR_COLS = 5;
     const FlowIterArgs& a = wa.a;
-    extern __shared__ __align__(128) unsigned char smem_win[];
-    unsigned char* smem_raw = smem_win;
-    double* tiles = reinterpret_cast<double*>(smem_raw);                       // [2][TR*5][LS]
-    float4* ringA = reinterpret_cast<float4*>(smem_raw + C::ringA_off);
-    float* ringB = reinterpret_cast<float*>(smem_raw + C::ringB_off);
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw + C::bar_off);
+    extern __shared__ __align__(128) unsigned char smem_ws[];
+    double* tiles = reinterpret_cast<double*>(smem_ws);                       // [2][TR*5][LS]
     const int h = a.h, w = a.w;
     const int t = threadIdx.x;
     const int k = blockIdx.x;  // strip
@@ -666,14 +499,6 @@ k_flow_iter_win(WinArgs wa)
     const int x0 = k * CW;
     const int ncols = min(CW, w - x0);   // multiple of 4
     const int ntiles = (h + TR - 1) / TR;
-
-    const uint32_t bar0 = smem_addr(bars);
-    if (t == 0) {
-#pragma unroll
-        for (int i = 0; i < C::NBAR; i++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar0 + 8 * i));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
 
     if (t >= NT) {
         // =============================== scan warp: phase H ===============================
@@ -754,10 +579,9 @@ k_flow_iter_win(WinArgs wa)
 
     // =============================== column warps: phases V and S ===============================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
-    // phase V: thread t <-> tile position t <-> image column x0 - m - 1 + t (clamped: replicated border)
-    const bool active = t < ncols + C::HALO;
+    // phase V: thread t <-> tile position t <-> image column x0 - m - 1 + t (clamped: replicated border); threads
+    // beyond the strip's halo work on a clamped column too, their results are never read
     const int xcl = min(max(x0 - m - 1 + t, 0), w - 1);
-    const bool colb = (unsigned)(xcl - 5) >= (unsigned)(w - 10);
     const float sxc = __fmul_rn(xcl < 5 ? (xcl < 2 ? 0.14f : 0.4472f) : 1.f,
                                 xcl >= w - 5 ? (w - xcl - 1 < 2 ? 0.14f : 0.4472f) : 1.f);
 
@@ -765,92 +589,31 @@ k_flow_iter_win(WinArgs wa)
     const float* R1 = a.R + (int64_t)a.map1.slot(b) * a.R_stride;
     const float4* R0a = reinterpret_cast<const float4*>(R0);
     const float* R0b = R0 + (int64_t)4 * h * w;
+    const float4* R1a = reinterpret_cast<const float4*>(R1);
+    const float* R1b = R1 + (int64_t)4 * h * w;
     const float2* fin = reinterpret_cast<const float2*>(a.flow_in) + (int64_t)b * h * w;
     float2* fout = reinterpret_cast<float2*>(a.flow_out) + (int64_t)b * h * w;
 
-    WinState ws;
-    ws.R1a = reinterpret_cast<const float4*>(R1);
-    ws.R1b = R1 + (int64_t)4 * h * w;
-    ws.ringA = ringA;
-    ws.ringB = ringB;
-    // Window geometry. Horizontally the window is centred on the strip's mean flow (centre.x, constant). Vertically
-    // it follows the flow: tile j reads R1 rows [A_j, A_j + WROWS), A_j = TR*j + m - HY + c_j, where the centre c_j
-    // is the rounded mean vertical flow of the tile's own rows (known one tile ahead: the rows are prefetched),
-    // limited to a change of one row per tile so that the ring (row y lives in ring row y mod NR) only ever grows
-    // at its lower end: the rows [B_{j+1}, B_{j+2}) are fetched after phase V of tile j, one mbarrier per tile.
-    const int2 centre = wa.centres[(int64_t)b * a.strips + k];
-    int* s_c = reinterpret_cast<int*>(smem_raw + C::bar_off + 8 * C::NBAR);        // [3] centres c_j by j % 3
-    float* s_part = reinterpret_cast<float*>(smem_raw + C::bar_off + 8 * C::NBAR + 16);   // [NT / 32] partial sums
-    ws.xs = x0 - C::XL + centre.x;
-    ws.ybase = m - C::HY + centre.y;
-    ws.rb = ((ws.ybase % C::NR) + C::NR) % C::NR;
-
-    // fetch R1 rows [lo, hi) x window columns (clipped to the image) into the ring; completion on mbarrier `slot`
-    const int cx0 = max(ws.xs, 0), cx1 = min(ws.xs + C::WW, w);
-    auto issue_rows = [&](int lo, int hi, int slot) {
-        const uint32_t bar = bar0 + 8 * slot;
-        const int vlo = max(lo, 0), vhi = min(hi, h);
-        const int cols = cx1 - cx0;
-        if (vhi <= vlo || cols <= 0) {
-            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
-            return;
-        }
-        const uint32_t bytes = (uint32_t)((vhi - vlo) * cols * 20);
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
-        int rr = vlo % C::NR;   // vlo >= 0
-        for (int yy = vlo; yy < vhi; yy++) {
-            const int so = rr * C::WW + (cx0 - ws.xs);
-            bulk_g2s(smem_addr(ringA + so), ws.R1a + ((int64_t)yy * w + cx0), (uint32_t)cols * 16, bar);
-            bulk_g2s(smem_addr(ringB + so), ws.R1b + ((int64_t)yy * w + cx0), (uint32_t)cols * 4, bar);
-            rr = rr + 1 == C::NR ? 0 : rr + 1;
-        }
-    };
-    auto wait_tile = [&](int j) { mbar_wait_parity(bar0 + 8 * (j % C::NBAR), (uint32_t)((j / C::NBAR) & 1)); };
-    // the issuing thread's bookkeeping: fetched up to row `fetched` (exclusive), centre of the last tile planned
-    int fetched = 0, c_last = centre.y;
-    if (t == NT - 1) {
-        const int A0 = m - C::HY + centre.y;
-        issue_rows(A0, A0 + C::WROWS, 0);                       // tile 0
-        issue_rows(A0 + C::WROWS, A0 + C::WROWS + TR, 1);       // tile 1, same centre
-        fetched = A0 + C::WROWS + TR;
-        s_c[0] = centre.y;
-        s_c[1] = centre.y;
-    }
-
+    // R0 / flow of one row of this thread's column: read once, streamed past L1's resident R1 rows
     auto load_row = [&](int y) {
         RowIn in;
         const int idx = min(y, h - 1) * w + xcl;
-        in.f = __ldg(fin + idx);
-        in.c03 = __ldg(R0a + idx);
-        in.c4 = __ldg(R0b + idx);
+        asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(in.f.x), "=f"(in.f.y) : "l"(fin + idx));
+        asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(in.c03.x), "=f"(in.c03.y), "=f"(in.c03.z), "=f"(in.c03.w) : "l"(R0a + idx));
+        asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(in.c4) : "l"(R0b + idx));
         return in;
     };
 
     float Mring[RR][5];
-    double vs[5] = {0, 0, 0, 0, 0};
-    RowIn pfa[TR];
-    // threads beyond the strip's halo run phase V on zero inputs (valid addresses, results never read)
-#pragma unroll
-    for (int r = 0; r < TR; r++) {
-        pfa[r].f = make_float2(0.f, 0.f);
-        pfa[r].c03 = make_float4(0.f, 0.f, 0.f, 0.f);
-        pfa[r].c4 = 0.f;
-    }
-#pragma unroll
-    for (int s = 0; s < RR; s++)
-#pragma unroll
-        for (int c = 0; c < 5; c++) Mring[s][c] = 0.f;
-
-    wait_tile(0);   // the rows of tile 0 also serve the seed rows below (where they do not, the global gather does)
-
-    if (active) {
+    double vs[5];
+    RowIn cur[TR];
+    {
         // rows 0 .. m-1 seed the column sums: vsum = M[0]*(m+2) + sum_{y=1}^{m-1} M[min(y,h-1)]
 #pragma unroll
         for (int y = 0; y < m; y++) {
             const RowIn in = load_row(y);
-            const M5 ms = win_matrices_px_slow<C>(in, ws, xcl, min(y, h - 1), h, w, colb, sxc, false);
-#pragma unroll
-            for (int c = 0; c < 5; c++) Mring[y][c] = ms.v[c];
+            ws_matrices_px<0>(in, R1a, R1b, xcl, min(y, h - 1), h, w, sxc, Mring[y]);
         }
         const float mp2 = (float)(m + 2);
 #pragma unroll
@@ -866,7 +629,7 @@ k_flow_iter_win(WinArgs wa)
 #pragma unroll
             for (int c = 0; c < 5; c++) Mring[s][c] = Mring[0][c];
 #pragma unroll
-        for (int r = 0; r < TR; r++) pfa[r] = load_row(r + m);
+        for (int r = 0; r < TR; r++) cur[r] = load_row(r + m);
     }
 
     // phase S of tile j (column t of the strip): regularised 2x2 solve in float64, flow written once. Full tiles run
@@ -896,59 +659,18 @@ k_flow_iter_win(WinArgs wa)
         }
     };
 
-    // one tile: phase V from `cur` (its R0 / flow rows, already in registers) while the rows of the tile after it
-    // are fetched into `nxt`; then phase S of the tile before it
-    auto tile_step = [&](int j, RowIn (&cur)[TR]) {
+    for (int j = 0; j < ntiles; j++) {
         const int y0 = j * TR;
         double* tq = tiles + (j & 1) * TR * 5 * LS + t;
-        if (j > 0) {
-            wait_tile(j);
-            const int cj = s_c[j % C::NBAR];
-            ws.ybase = y0 + m - C::HY + cj;
-            ws.rb = ((ws.ybase % C::NR) + C::NR) % C::NR;
-        }
+        // ---------------- phase V ----------------
 #pragma unroll
         for (int half = 0; half < 2; half++) {
-            // The SR rows of a half are independent up to the column sums: one straight-line block (the compiler
-            // interleaves the rows) that gathers from the window. Pixels whose taps leave the window (sparse: flow
-            // outliers) are then redone, lane by lane, by the out-of-line function with the global gather.
-            // (threads beyond the halo carry zero flows: they never ask for the global gather)
-            bool miss[SR];
-            bool anymiss = false;
-#pragma unroll
-            for (int rr = 0; rr < SR; rr++) {
-                const int r = half * SR + rr;
-                const int yn = min(y0 + r + m, h - 1);
-                miss[rr] = active && win_needs_global<C, C::WROWS>(cur[r], ws, xcl, yn, h, w);
-                anymiss |= miss[rr];
-            }
-            anymiss = __any_sync(0xffffffffu, anymiss);
-            if (wa.exp & 64) {
-                const unsigned bm = __ballot_sync(0xffffffffu, miss[0] || miss[1] || miss[2]);
-                if ((t & 31) == 0) {
-                    atomicAdd(&g_win_dbg[0], 1ull);
-                    if (anymiss) atomicAdd(&g_win_dbg[1], 1ull);
-                    atomicAdd(&g_win_dbg[2], (unsigned long long)__popc(bm));
-                }
-            }
+            // the SR rows of a half are independent up to the column sums: one straight-line block
             float Mv[SR][5];
 #pragma unroll
             for (int rr = 0; rr < SR; rr++) {
                 const int r = half * SR + rr;
-                const int yn = min(y0 + r + m, h - 1);
-                win_matrices_px<C, C::WROWS, true>(cur[r], ws, xcl, yn, h, w, colb, sxc, Mv[rr]);
-            }
-            if (anymiss) {
-#pragma unroll
-                for (int rr = 0; rr < SR; rr++) {
-                    if (miss[rr]) {
-                        const int r = half * SR + rr;
-                        const int yn = min(y0 + r + m, h - 1);
-                        const M5 ms = win_matrices_px_slow<C>(cur[r], ws, xcl, yn, h, w, colb, sxc, half == 1);
-#pragma unroll
-                        for (int c = 0; c < 5; c++) Mv[rr][c] = ms.v[c];
-                    }
-                }
+                ws_matrices_px<FDN_WS_PF>(cur[r], R1a, R1b, xcl, min(y0 + r + m, h - 1), h, w, sxc, Mv[rr]);
             }
             if (!(wa.exp & 4)) {
 #pragma unroll
@@ -965,10 +687,8 @@ k_flow_iter_win(WinArgs wa)
                 }
             }
             // R0 / flow of the same rows of the NEXT tile: in flight for a whole tile period
-            if (active) {
 #pragma unroll
-                for (int rr = 0; rr < SR; rr++) cur[half * SR + rr] = load_row(y0 + TR + half * SR + rr + m);
-            }
+            for (int rr = 0; rr < SR; rr++) cur[half * SR + rr] = load_row(y0 + TR + half * SR + rr + m);
         }
         __threadfence_block();
         nbar_arrive(BAR_FULL + (j & 1), NT + 32);          // the scan warp may start on tile j
@@ -976,36 +696,9 @@ k_flow_iter_win(WinArgs wa)
             nbar_sync(BAR_DONE + ((j - 1) & 1), NT + 32);  // scan of tile j-1 finished
             phase_s(j - 1);
         }
-        // mean vertical flow of the NEXT tile's rows (in `cur` by now): where the tile after it centres its window
-        {
-            float sy = 0.f;
-            if (active) {
-#pragma unroll
-                for (int r = 0; r < TR; r++) sy += cur[r].f.y;
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) sy += __shfl_xor_sync(0xffffffffu, sy, o);
-            if ((t & 31) == 0) s_part[(j & 1) * (NT / 32) + (t >> 5)] = sy;
-        }
-        // every column warp is past phase V of tile j (its window rows above A_{j+1} are no longer read) and past
-        // phase S of tile j-1 (whose shared-memory tile phase V of tile j+1 overwrites)
+        // every column warp is past phase S of tile j-1, whose shared-memory tile phase V of tile j+1 overwrites
         nbar_sync(BAR_COLS, NT);
-        if (t == NT - 1) {
-            float sy = 0.f;
-#pragma unroll
-            for (int i = 0; i < NT / 32; i++) sy += s_part[(j & 1) * (NT / 32) + i];
-            sy = sy / (float)((ncols + C::HALO) * TR);
-            int c = fabsf(sy) < 1e6f ? (int)rintf(sy) : c_last;
-            c = min(max(c, c_last - 1), c_last + 1);
-            c_last = c;
-            const int Bnext = (j + 2) * TR + m - C::HY + c + C::WROWS;   // B_{j+2}
-            issue_rows(fetched, Bnext, (j + 2) % C::NBAR);
-            fetched = max(fetched, Bnext);
-            s_c[(j + 2) % C::NBAR] = c;
-        }
-    };
-
-    for (int j = 0; j < ntiles; j++) tile_step(j, pfa);
+    }
     nbar_sync(BAR_DONE + ((ntiles - 1) & 1), NT + 32);
     phase_s(ntiles - 1);
 }
@@ -1018,30 +711,28 @@ static unsigned long long g_flow_epoch = 1;
 // compare below the current one); the carry area is rewritten by every launch before it is read.
 static int strip_width(int w) { return w > 96 ? 128 : 32; }
 
-// strips of the windowed kernel (k_flow_iter_win): CW = multiple of 4, <= WinCfg::CWMAX
+// strips of k_flow_iter_ws: CW = multiple of 4, <= WsCfg::CWMAX
 static int win_strip_width(int w, int cwmax)
 {
     const int strips = (int)cdiv(w, cwmax);
     return (int)((cdiv(w, strips) + 3) / 4 * 4);
 }
 #define FDN_WIN_NT 128
-typedef WinCfg<2, FDN_WIN_NT> WinCfg2;
+typedef WsCfg<2, FDN_WIN_NT> WinCfg2;
 
 static size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 static size_t flow_flag_bytes(int n) { return align256(sizeof(unsigned long long) * (size_t)n * FDN_MAX_STRIPS); }
-static size_t flow_offset_bytes(int n) { return align256(sizeof(int2) * (size_t)n * FDN_MAX_STRIPS); }   // window centres
 static size_t flow_carry_bytes(int n, int h, int w)   // k_flow_iter: one double per (pair, strip, row, channel)
 {
     return align256(sizeof(double) * 5 * (size_t)n * (size_t)cdiv(w, strip_width(w)) * h);
 }
-static size_t flow_packet_bytes(int n, int h, int w)  // k_flow_iter_win: one 16-byte packet pair per carry
+static size_t flow_packet_bytes(int n, int h, int w)  // k_flow_iter_ws: one 16-byte packet pair per carry
 {
     const size_t strips = (size_t)cdiv(w, win_strip_width(w, WinCfg2::CWMAX));
     return align256(sizeof(ulonglong2) * 5 * (size_t)n * strips * h);
 }
 
-// Scratch layout: [flags: n * MAX_STRIPS u64][window centres: n * MAX_STRIPS int2][packets of k_flow_iter_win ...  ... carries of
-// k_flow_iter]. The flag
+// Scratch layout: [flags: n * MAX_STRIPS u64][packets of k_flow_iter_ws ...  ... carries of k_flow_iter]. The flag
 // area has the same place and size for every pyramid level that shares the scratch (it only ever holds epochs of
 // earlier launches, which compare below the current one). Packets grow from the front and plain carries sit at the
 // END of the scratch, so a level run by one kernel never writes into the area the other kernel polls at another
@@ -1049,7 +740,7 @@ static size_t flow_packet_bytes(int n, int h, int w)  // k_flow_iter_win: one 16
 // reads them.
 size_t flow_iter_scratch_bytes(int n, int h, int w)
 {
-    return flow_flag_bytes(n) + flow_offset_bytes(n) + flow_packet_bytes(n, h, w) + flow_carry_bytes(n, h, w);
+    return flow_flag_bytes(n) + flow_packet_bytes(n, h, w) + flow_carry_bytes(n, h, w);
 }
 
 int flow_iter_scratch_init(void* scratch, size_t bytes, cudaStream_t st)
@@ -1099,29 +790,29 @@ int launch_flow_iter(const float* R, int64_t R_stride, SlotMap map0, SlotMap map
     a.carry = reinterpret_cast<double*>(static_cast<char*>(scratch) + scratch_bytes - flow_carry_bytes(n, h, w));
     const size_t smem = sizeof(double) * TR * 5 * a.LS + sizeof(float) * RR * 5 * NT;
     const unsigned long long tiles = (unsigned long long)cdiv(h, TR);
-    // windowed variant (default for winsize 5 on images that are not tiny); FDN_FLOW_ITER=old keeps k_flow_iter
+    // warp-specialised variant (default for winsize 5 on images that are not tiny); FDN_FLOW_ITER=old keeps k_flow_iter
     const char* env_variant = getenv("FDN_FLOW_ITER");   // read per launch: tests flip it to compare both kernels
     const int variant = (env_variant && strcmp(env_variant, "old") == 0) ? 0 : 1;
     const bool win = variant == 1 && m == 2 && w % 4 == 0 && w >= 64 && h >= 16 &&
                      (reinterpret_cast<uintptr_t>(R) & 15) == 0 && R_stride % 4 == 0;
     if (win) {
-        WinArgs wa;
+        WsArgs wa;
         wa.CW = win_strip_width(w, WinCfg2::CWMAX);
         a.strips = (int)cdiv(w, wa.CW);
         FDN_CHECK_ARG(a.strips <= FDN_MAX_STRIPS, "image too wide (%d strips)", a.strips);
-        wa.centres = reinterpret_cast<int2*>(static_cast<char*>(scratch) + flow_flag_bytes(n));
-        wa.packets = reinterpret_cast<ulonglong2*>(static_cast<char*>(scratch) + flow_flag_bytes(n) + flow_offset_bytes(n));
+        wa.packets = reinterpret_cast<ulonglong2*>(static_cast<char*>(scratch) + flow_flag_bytes(n));
         static bool attr_set = false;
         if (!attr_set) {
-            FDN_CUDA(cudaFuncSetAttribute(k_flow_iter_win<2, FDN_WIN_NT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            FDN_CUDA(cudaFuncSetAttribute(k_flow_iter_ws<2, FDN_WIN_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)WinCfg2::smem_bytes));
-            FDN_CUDA(cudaFuncSetAttribute(k_flow_iter_win<2, FDN_WIN_NT, 2>,
-                                          cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            // leave the rest of the SM's L1/shared array to L1: the R1 rows a strip walks over live there
+            FDN_CUDA(cudaFuncSetAttribute(k_flow_iter_ws<2, FDN_WIN_NT>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                          (int)((2 * (WinCfg2::smem_bytes + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024))));
             if (getenv("FDN_DEBUG")) {
                 int nb = 0;
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_flow_iter_win<2, FDN_WIN_NT, 2>, FDN_WIN_NT + 128,
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_flow_iter_ws<2, FDN_WIN_NT>, FDN_WIN_NT + 128,
                                                               WinCfg2::smem_bytes);
-                fprintf(stderr, "[fdn] k_flow_iter_win: %d blocks/SM, %zu B shared memory per block\n", nb,
+                fprintf(stderr, "[fdn] k_flow_iter_ws: %d blocks/SM, %zu B shared memory per block\n", nb,
                         (size_t)WinCfg2::smem_bytes);
             }
             attr_set = true;
@@ -1138,25 +829,12 @@ int launch_flow_iter(const float* R, int64_t R_stride, SlotMap map0, SlotMap map
             a.epoch = g_flow_epoch;
             wa.a = a;
             ProfScope ps(K_FLOW_ITER, 56.0 * nb * h * w, st);
-            k_flow_centre<<<dim3((unsigned)a.strips, (unsigned)nb), 256, 0, st>>>(reinterpret_cast<const float2*>(a.flow_in), h, w,
-                                                                                 wa.CW, wa.centres);
-            FDN_LAUNCHED("k_flow_centre");
             dim3 grid((unsigned)a.strips, (unsigned)nb);
-            k_flow_iter_win<2, FDN_WIN_NT, 2><<<grid, FDN_WIN_NT + 128, WinCfg2::smem_bytes, st>>>(wa);
-            FDN_LAUNCHED("k_flow_iter_win");
+            k_flow_iter_ws<2, FDN_WIN_NT><<<grid, FDN_WIN_NT + 128, WinCfg2::smem_bytes, st>>>(wa);
+            FDN_LAUNCHED("k_flow_iter_ws");
             wa.packets += (int64_t)nb * a.strips * h * 5;
-            wa.centres += (int64_t)nb * a.strips;
         }
         g_flow_epoch += tiles + 1;
-        if (wa.exp & 64) {
-            unsigned long long c[4];
-            cudaStreamSynchronize(st);
-            cudaMemcpyFromSymbol(c, g_win_dbg, sizeof c);
-            fprintf(stderr, "[fdn] win h=%d w=%d n=%d: warp-halves %llu, with misses %llu (%.2f%%), missing lanes %llu\n", h, w, n,
-                    c[0], c[1], c[0] ? 100.0 * c[1] / c[0] : 0.0, c[2]);
-            unsigned long long z[4] = {0, 0, 0, 0};
-            cudaMemcpyToSymbol(g_win_dbg, z, sizeof z);
-        }
         return FDN_OK;
     }
     for (int b0 = 0; b0 < n; b0 += 65535) {
