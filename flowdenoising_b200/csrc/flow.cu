@@ -388,16 +388,40 @@ struct WsCfg {
     static constexpr int HALO = 2 * MT + 1;
     static constexpr int CWMAX = (NT - HALO) & ~3;
     static constexpr int LS = NT + 1;       // tile line stride in doubles (== 1 mod 16)
-    static constexpr size_t smem_bytes = 2 * sizeof(double) * TR * 5 * LS;   // two tiles
+    static constexpr size_t tiles_bytes = 2 * sizeof(double) * TR * 5 * LS;   // two tiles
+    static constexpr size_t smem_bytes = tiles_bytes + 16;                    // + the scan's progress counters
     static_assert(LS % 16 == 1, "tile line stride must be 1 mod 16 doubles");
     static_assert(5 * TR <= 32, "phase H runs in one warp");
 };
 
-// M of one pixel, branch-free: the bilinear taps are read at clamped (always valid) positions and discarded by a
-// select when the displaced position lies outside the image, exactly as the branch of update_matrices_px would.
+// The eight bilinear taps of one pixel (R1 at the displaced position), read at clamped -- always valid -- positions.
+struct Taps {
+    float4 p00, p01, p10, p11;
+    float q00, q01, q10, q11;
+};
+
 template <int PF>
-__device__ __forceinline__ void ws_matrices_px(const RowIn& in, const float4* __restrict__ R1a,
-                                               const float* __restrict__ R1b, int x, int y, int h, int w, float sxc,
+__device__ __forceinline__ Taps ws_gather(const float2 f, const float4* __restrict__ R1a, const float* __restrict__ R1b,
+                                          int x, int y, int h, int w)
+{
+    const int x1 = (int)floorf(__fadd_rn((float)x, f.x)), y1 = (int)floorf(__fadd_rn((float)y, f.y));
+    const int yc = min(max(y1, 0), h - 2), xc = min(max(x1, 0), w - 2);
+    const int g = yc * w + xc;
+    if (PF > 0) {
+        // warm L1 with the R1 rows this column will gather from PF rows further down (the flow is smooth)
+        const int gp = min(yc + PF + 1, h - 1) * w + xc;
+        asm volatile("prefetch.global.L1 [%0];" :: "l"(R1a + gp));
+        asm volatile("prefetch.global.L1 [%0];" :: "l"(R1b + gp));
+    }
+    Taps t;
+    t.p00 = __ldg(R1a + g); t.p01 = __ldg(R1a + g + 1); t.p10 = __ldg(R1a + g + w); t.p11 = __ldg(R1a + g + w + 1);
+    t.q00 = __ldg(R1b + g); t.q01 = __ldg(R1b + g + 1); t.q10 = __ldg(R1b + g + w); t.q11 = __ldg(R1b + g + w + 1);
+    return t;
+}
+
+// M of one pixel, branch-free: the taps are discarded by a select when the displaced position lies outside the
+// image, exactly as the branch of update_matrices_px would.
+__device__ __forceinline__ void ws_matrices_px(const RowIn& in, const Taps& tp, int x, int y, int h, int w, float sxc,
                                                float M[5])
 {
     const float dx = in.f.x, dy = in.f.y;
@@ -408,25 +432,15 @@ __device__ __forceinline__ void ws_matrices_px(const RowIn& in, const float4* __
     const float4 c03 = in.c03;
     const float c4 = in.c4;
     const bool in_img = (unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1);
-    const int yc = min(max(y1, 0), h - 2), xc = min(max(x1, 0), w - 2);
-    const int g = yc * w + xc;
-    if (PF > 0) {
-        // warm L1 with the R1 rows this column will gather from PF rows further down (the flow is smooth)
-        const int gp = min(yc + PF + 1, h - 1) * w + xc;
-        asm volatile("prefetch.global.L1 [%0];" :: "l"(R1a + gp));
-        asm volatile("prefetch.global.L1 [%0];" :: "l"(R1b + gp));
-    }
-    const float4 p00 = __ldg(R1a + g), p01 = __ldg(R1a + g + 1), p10 = __ldg(R1a + g + w), p11 = __ldg(R1a + g + w + 1);
-    const float q00 = __ldg(R1b + g), q01 = __ldg(R1b + g + 1), q10 = __ldg(R1b + g + w), q11 = __ldg(R1b + g + w + 1);
     const float ofx = __fsub_rn(1.f, fx), ofy = __fsub_rn(1.f, fy);
     const float a00 = __fmul_rn(ofx, ofy), a01 = __fmul_rn(fx, ofy), a10 = __fmul_rn(ofx, fy), a11 = __fmul_rn(fx, fy);
 #define FDN_BILIN(v00, v01, v10, v11) \
     __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a00, v00), __fmul_rn(a01, v01)), __fmul_rn(a10, v10)), __fmul_rn(a11, v11))
-    float r2 = FDN_BILIN(p00.x, p01.x, p10.x, p11.x);
-    float r3 = FDN_BILIN(p00.y, p01.y, p10.y, p11.y);
-    float r4 = FDN_BILIN(p00.z, p01.z, p10.z, p11.z);
-    float r5 = FDN_BILIN(p00.w, p01.w, p10.w, p11.w);
-    float r6 = FDN_BILIN(q00, q01, q10, q11);
+    float r2 = FDN_BILIN(tp.p00.x, tp.p01.x, tp.p10.x, tp.p11.x);
+    float r3 = FDN_BILIN(tp.p00.y, tp.p01.y, tp.p10.y, tp.p11.y);
+    float r4 = FDN_BILIN(tp.p00.z, tp.p01.z, tp.p10.z, tp.p11.z);
+    float r5 = FDN_BILIN(tp.p00.w, tp.p01.w, tp.p10.w, tp.p11.w);
+    float r6 = FDN_BILIN(tp.q00, tp.q01, tp.q10, tp.q11);
 #undef FDN_BILIN
     r4 = __fmul_rn(__fadd_rn(c03.z, r4), 0.5f);
     r5 = __fmul_rn(__fadd_rn(c03.w, r5), 0.5f);
@@ -454,6 +468,9 @@ __device__ __forceinline__ void ws_matrices_px(const RowIn& in, const float4* __
     M[4] = __fadd_rn(__fmul_rn(r6, r2), __fmul_rn(r5, r3));
 }
 
+#ifndef FDN_WS_HC
+#define FDN_WS_HC 8
+#endif
 #ifndef FDN_WS_PF
 #define FDN_WS_PF 6
 #endif
@@ -487,10 +504,11 @@ k_flow_iter_ws(WsArgs wa)
 {
     using C = WsCfg<MT, NT_>;
     constexpr int NT = C::NT, TR = C::TR, SR = C::SR, RR = C::TR, LS = C::LS, m = MT;
-    constexpr int BAR_FULL = 1, BAR_DONE = 3, BAR_COLS = 5;
+    constexpr int BAR_FULL = 1, BAR_FREE = 5;
     const FlowIterArgs& a = wa.a;
     extern __shared__ __align__(128) unsigned char smem_ws[];
     double* tiles = reinterpret_cast<double*>(smem_ws);                       // [2][TR*5][LS]
+    volatile int* prog = reinterpret_cast<volatile int*>(smem_ws + C::tiles_bytes);   // [2]: j * 4096 + columns scanned
     const int h = a.h, w = a.w;
     const int t = threadIdx.x;
     const int k = blockIdx.x;  // strip
@@ -500,30 +518,77 @@ k_flow_iter_ws(WsArgs wa)
     const int ncols = min(CW, w - x0);   // multiple of 4
     const int ntiles = (h + TR - 1) / TR;
 
+    if (t < 2) prog[t] = -1;
+    __syncthreads();
+
     if (t >= NT) {
         // =============================== scan warp: phase H ===============================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
-        if (t >= NT + 32) return;   // the scan warpgroup has one working warp
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+        if (t >= NT + 32) {
+            // =============================== solve warps: phase S ===============================
+            // regularised 2x2 solve in float64, flow written once. Full tiles run as one straight-line block (the
+            // rows are independent: the compiler interleaves their dependency chains).
+            constexpr int NS = 96;   // solving lanes
+            const int sl = t - (NT + 32);
+            float2* fout = reinterpret_cast<float2*>(a.flow_out) + (int64_t)b * h * w;
+            auto solve_px = [&](const double* tt, int r, float2* dst) {
+                double g[5];
+#pragma unroll
+                for (int c = 0; c < 5; c++) g[c] = __dmul_rn(tt[(r * 5 + c) * LS], a.scale);
+                const double det = __dadd_rn(__dsub_rn(__dmul_rn(g[0], g[2]), __dmul_rn(g[1], g[1])), 1e-3);
+                const double idet = __drcp_rn(det);  // == 1./det correctly rounded, like the IEEE division
+                float2 o;
+                o.x = (float)__dmul_rn(__dsub_rn(__dmul_rn(g[0], g[4]), __dmul_rn(g[1], g[3])), idet);
+                o.y = (float)__dmul_rn(__dsub_rn(__dmul_rn(g[2], g[3]), __dmul_rn(g[1], g[4])), idet);
+                *dst = o;
+            };
+            const int sw = sl >> 5, sln = sl & 31;
+            for (int j = 0; j < ntiles; j++) {
+                const int y0 = j * TR;
+                // the solve follows the scan through the tile: 32-column chunk q goes to solve warp q % 3 as soon as the
+                // scan warp has published that many columns
+                for (int q = sw; q * 32 < ncols; q += NS / 32) {
+                    const int need = j * 4096 + min(q * 32 + 32, ncols);
+                    while (prog[j & 1] < need) __nanosleep(20);
+                    __threadfence_block();
+                    const int col = q * 32 + sln;
+                    if (col < ncols && !(wa.exp & 8)) {
+                        const double* tt = tiles + (j & 1) * TR * 5 * LS + col;
+                        float2* dst = fout + (int64_t)y0 * w + x0 + col;
+                        if (y0 + TR <= h) {
+#pragma unroll
+                            for (int r = 0; r < TR; r++) solve_px(tt, r, dst + r * w);
+                        } else {
+                            for (int r = 0; r < h - y0; r++) solve_px(tt, r, dst + r * w);
+                        }
+                    }
+                }
+                nbar_arrive(BAR_FREE + (j & 1), NS + NT);     // the tile may be overwritten by phase V of tile j+2
+            }
+            return;
+        }
         const int lane = t - NT;
         const int r = lane / 5, c = lane - r * 5;
         ulonglong2* pk_out = wa.packets + ((int64_t)b * a.strips + k) * h * 5;
         const ulonglong2* pk_in = wa.packets + ((int64_t)b * a.strips + max(k - 1, 0)) * h * 5;
         constexpr int off = 2 * m + 1;
+        constexpr int HC = FDN_WS_HC;   // columns per chunk of the scan
         for (int j = 0; j < ntiles; j++) {
             const int y = j * TR + r;
             nbar_sync(BAR_FULL + (j & 1), NT + 32);
+            const unsigned hmask = __ballot_sync(0xffffffffu, lane < 5 * TR && y < h);   // the scanning lanes
             if (lane < 5 * TR && y < h) {
                 double* line = tiles + ((j & 1) * TR * 5 + r * 5 + c) * LS;
                 // S(i) = S(i-1) + (vs[i+m] - vs[i-m-1]); S(i) overwrites the dead slot of column i-m-1.
                 // Chunks of 8 columns: the differences of the next chunk are formed before the chain of this one
                 // and the 8 sums are stored after it.
-                double da[8], db[8], sv[8];
+                double da[HC], db[HC], sv[HC];
 #define FDN_DIFF8(D, base)                                                        \
-    _Pragma("unroll") for (int u = 0; u < 8; u++) D[u] = __dsub_rn(line[(base) + u + off], line[(base) + u]);
+    _Pragma("unroll") for (int u = 0; u < HC; u++) D[u] = __dsub_rn(line[(base) + u + off], line[(base) + u]);
 #define FDN_CHAIN8(D, base)                                                       \
-    _Pragma("unroll") for (int u = 0; u < 8; u++) { S = __dadd_rn(S, D[u]); sv[u] = S; } \
-    _Pragma("unroll") for (int u = 0; u < 8; u++) line[(base) + u] = sv[u];
-                const int n8 = ncols >> 3;   // full chunks; ncols % 8 is 0 or 4
+    _Pragma("unroll") for (int u = 0; u < HC; u++) { S = __dadd_rn(S, D[u]); sv[u] = S; } \
+    _Pragma("unroll") for (int u = 0; u < HC; u++) line[(base) + u] = sv[u];
+                const int n8 = ncols / HC;   // full chunks; ncols % 8 is 0 or 4
                 if (n8 > 0) FDN_DIFF8(da, 0);
                 double S;
                 if (k == 0) {
@@ -541,19 +606,25 @@ k_flow_iter_ws(WsArgs wa)
                     }
                     S = __hiloint2double((int)(unsigned)v.y, (int)(unsigned)v.x);
                 }
+                __syncwarp(hmask);   // the lanes leave their polling loops one by one: scan in lockstep from here on
                 if (!(wa.exp & 1)) {
                     int i = 0, c8 = 0;
                     while (c8 < n8) {
-                        if (c8 + 1 < n8) FDN_DIFF8(db, i + 8);
+                        if (c8 + 1 < n8) FDN_DIFF8(db, i + HC);
                         FDN_CHAIN8(da, i);
-                        i += 8;
+                        i += HC;
                         if (++c8 == n8) break;
-                        if (c8 + 1 < n8) FDN_DIFF8(da, i + 8);
+                        if (c8 + 1 < n8) FDN_DIFF8(da, i + HC);
                         FDN_CHAIN8(db, i);
-                        i += 8;
+                        i += HC;
                         ++c8;
+                        if ((i & 31) == 0) {   // every 32 columns: let the solve warps follow
+                            __syncwarp(hmask);
+                            __threadfence_block();
+                            if (lane == 0) prog[j & 1] = j * 4096 + i;
+                        }
                     }
-                    if (ncols & 4) {
+                    if (HC == 8 && (ncols & 4)) {
 #pragma unroll
                         for (int u = 0; u < 4; u++) da[u] = __dsub_rn(line[i + u + off], line[i + u]);
 #pragma unroll
@@ -572,13 +643,13 @@ k_flow_iter_ws(WsArgs wa)
             }
             __syncwarp();
             __threadfence_block();
-            nbar_arrive(BAR_DONE + (j & 1), NT + 32);
+            if (lane == 0) prog[j & 1] = j * 4096 + 4095;   // the whole tile is scanned
         }
         return;
     }
 
     // =============================== column warps: phases V and S ===============================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 184;");
     // phase V: thread t <-> tile position t <-> image column x0 - m - 1 + t (clamped: replicated border); threads
     // beyond the strip's halo work on a clamped column too, their results are never read
     const int xcl = min(max(x0 - m - 1 + t, 0), w - 1);
@@ -592,16 +663,15 @@ k_flow_iter_ws(WsArgs wa)
     const float4* R1a = reinterpret_cast<const float4*>(R1);
     const float* R1b = R1 + (int64_t)4 * h * w;
     const float2* fin = reinterpret_cast<const float2*>(a.flow_in) + (int64_t)b * h * w;
-    float2* fout = reinterpret_cast<float2*>(a.flow_out) + (int64_t)b * h * w;
 
     // R0 / flow of one row of this thread's column: read once, streamed past L1's resident R1 rows
     auto load_row = [&](int y) {
         RowIn in;
         const int idx = min(y, h - 1) * w + xcl;
-        asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(in.f.x), "=f"(in.f.y) : "l"(fin + idx));
-        asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+        asm("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(in.f.x), "=f"(in.f.y) : "l"(fin + idx));
+        asm("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
                      : "=f"(in.c03.x), "=f"(in.c03.y), "=f"(in.c03.z), "=f"(in.c03.w) : "l"(R0a + idx));
-        asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(in.c4) : "l"(R0b + idx));
+        asm("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(in.c4) : "l"(R0b + idx));
         return in;
     };
 
@@ -613,7 +683,8 @@ k_flow_iter_ws(WsArgs wa)
 #pragma unroll
         for (int y = 0; y < m; y++) {
             const RowIn in = load_row(y);
-            ws_matrices_px<0>(in, R1a, R1b, xcl, min(y, h - 1), h, w, sxc, Mring[y]);
+            const Taps tp = ws_gather<0>(in.f, R1a, R1b, xcl, min(y, h - 1), h, w);
+            ws_matrices_px(in, tp, xcl, min(y, h - 1), h, w, sxc, Mring[y]);
         }
         const float mp2 = (float)(m + 2);
 #pragma unroll
@@ -632,45 +703,26 @@ k_flow_iter_ws(WsArgs wa)
         for (int r = 0; r < TR; r++) cur[r] = load_row(r + m);
     }
 
-    // phase S of tile j (column t of the strip): regularised 2x2 solve in float64, flow written once. Full tiles run
-    // as one straight-line block (the rows are independent: the compiler interleaves their dependency chains).
-    auto solve_px = [&](const double* tt, int r, float2* dst) {
-        double g[5];
-#pragma unroll
-        for (int c = 0; c < 5; c++) g[c] = __dmul_rn(tt[(r * 5 + c) * LS], a.scale);
-        const double det = __dadd_rn(__dsub_rn(__dmul_rn(g[0], g[2]), __dmul_rn(g[1], g[1])), 1e-3);
-        const double idet = __drcp_rn(det);  // == 1./det correctly rounded, like the IEEE division
-        float2 o;
-        o.x = (float)__dmul_rn(__dsub_rn(__dmul_rn(g[0], g[4]), __dmul_rn(g[1], g[3])), idet);
-        o.y = (float)__dmul_rn(__dsub_rn(__dmul_rn(g[2], g[3]), __dmul_rn(g[1], g[4])), idet);
-        *dst = o;
-    };
-    auto phase_s = [&](int j) {
-        if (t < ncols && !(wa.exp & 8)) {
-            const int y0 = j * TR;
-            const double* tt = tiles + (j & 1) * TR * 5 * LS + t;
-            float2* dst = fout + (int64_t)y0 * w + x0 + t;
-            if (y0 + TR <= h) {
-#pragma unroll
-                for (int r = 0; r < TR; r++) solve_px(tt, r, dst + r * w);
-            } else {
-                for (int r = 0; r < h - y0; r++) solve_px(tt, r, dst + r * w);
-            }
-        }
-    };
-
     for (int j = 0; j < ntiles; j++) {
         const int y0 = j * TR;
         double* tq = tiles + (j & 1) * TR * 5 * LS + t;
+        if (j >= 2) nbar_sync(BAR_FREE + (j & 1), 96 + NT);   // tile j-2 has been solved: its shared-memory tile is free
         // ---------------- phase V ----------------
 #pragma unroll
         for (int half = 0; half < 2; half++) {
-            // the SR rows of a half are independent up to the column sums: one straight-line block
+            // the SR rows of a half are independent up to the column sums: one straight-line block (all the gathers
+            // first, then the arithmetic of the rows interleaved by the compiler)
+            Taps tp[SR];
+#pragma unroll
+            for (int rr = 0; rr < SR; rr++) {
+                const int r = half * SR + rr;
+                tp[rr] = ws_gather<FDN_WS_PF>(cur[r].f, R1a, R1b, xcl, min(y0 + r + m, h - 1), h, w);
+            }
             float Mv[SR][5];
 #pragma unroll
             for (int rr = 0; rr < SR; rr++) {
                 const int r = half * SR + rr;
-                ws_matrices_px<FDN_WS_PF>(cur[r], R1a, R1b, xcl, min(y0 + r + m, h - 1), h, w, sxc, Mv[rr]);
+                ws_matrices_px(cur[r], tp[rr], xcl, min(y0 + r + m, h - 1), h, w, sxc, Mv[rr]);
             }
             if (!(wa.exp & 4)) {
 #pragma unroll
@@ -692,24 +744,13 @@ k_flow_iter_ws(WsArgs wa)
         }
         __threadfence_block();
         nbar_arrive(BAR_FULL + (j & 1), NT + 32);          // the scan warp may start on tile j
-        if (j > 0) {
-            nbar_sync(BAR_DONE + ((j - 1) & 1), NT + 32);  // scan of tile j-1 finished
-            phase_s(j - 1);
-        }
-        // every column warp is past phase S of tile j-1, whose shared-memory tile phase V of tile j+1 overwrites
-        nbar_sync(BAR_COLS, NT);
     }
-    nbar_sync(BAR_DONE + ((ntiles - 1) & 1), NT + 32);
-    phase_s(ntiles - 1);
 }
 
 static unsigned long long g_flow_epoch = 1;
 #define FDN_MAX_STRIPS 64
 
-// Scratch layout: [flags: n * MAX_STRIPS u64][carries: n * strips * h * 5 f64]. The flag area has the same place
-// and size for every pyramid level that shares the scratch (it only ever holds epochs of earlier launches, which
-// compare below the current one); the carry area is rewritten by every launch before it is read.
-static int strip_width(int w) { return w > 96 ? 128 : 32; }
+static int strip_width(int w) { return w > 96 ? 128 : 32; }   // k_flow_iter
 
 // strips of k_flow_iter_ws: CW = multiple of 4, <= WsCfg::CWMAX
 static int win_strip_width(int w, int cwmax)
