@@ -387,10 +387,9 @@ struct WsCfg {
     static constexpr int SR = MT + 1;       // rows per straight-line block
     static constexpr int HALO = 2 * MT + 1;
     static constexpr int CWMAX = (NT - HALO) & ~3;
-    static constexpr int LS = NT + 1;       // tile line stride in doubles (== 1 mod 16)
-    static constexpr size_t tiles_bytes = 2 * sizeof(double) * TR * 5 * LS;   // two tiles
+    static constexpr int LS = NT + 2;       // tile line stride in doubles (even: every line is 16-byte aligned)
+    static constexpr size_t tiles_bytes = 2 * sizeof(double) * TR * 5 * LS + 128;   // two tiles (+ the scan's read-ahead past the last line)
     static constexpr size_t smem_bytes = tiles_bytes + 16;                    // + the scan's progress counters
-    static_assert(LS % 16 == 1, "tile line stride must be 1 mod 16 doubles");
     static_assert(5 * TR <= 32, "phase H runs in one warp");
 };
 
@@ -523,7 +522,7 @@ k_flow_iter_ws(WsArgs wa)
 
     if (t >= NT) {
         // =============================== scan warp: phase H ===============================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
         if (t >= NT + 32) {
             // =============================== solve warps: phase S ===============================
             // regularised 2x2 solve in float64, flow written once. Full tiles run as one straight-line block (the
@@ -579,17 +578,35 @@ k_flow_iter_ws(WsArgs wa)
             const unsigned hmask = __ballot_sync(0xffffffffu, lane < 5 * TR && y < h);   // the scanning lanes
             if (lane < 5 * TR && y < h) {
                 double* line = tiles + ((j & 1) * TR * 5 + r * 5 + c) * LS;
+                double2* l2 = reinterpret_cast<double2*>(line);   // 16-byte aligned (LS is even)
                 // S(i) = S(i-1) + (vs[i+m] - vs[i-m-1]); S(i) overwrites the dead slot of column i-m-1.
-                // Chunks of 8 columns: the differences of the next chunk are formed before the chain of this one
-                // and the 8 sums are stored after it.
-                double da[HC], db[HC], sv[HC];
-#define FDN_DIFF8(D, base)                                                        \
-    _Pragma("unroll") for (int u = 0; u < HC; u++) D[u] = __dsub_rn(line[(base) + u + off], line[(base) + u]);
-#define FDN_CHAIN8(D, base)                                                       \
-    _Pragma("unroll") for (int u = 0; u < HC; u++) { S = __dadd_rn(S, D[u]); sv[u] = S; } \
-    _Pragma("unroll") for (int u = 0; u < HC; u++) line[(base) + u] = sv[u];
-                const int n8 = ncols / HC;   // full chunks; ncols % 8 is 0 or 4
-                if (n8 > 0) FDN_DIFF8(da, 0);
+                // The line is read ONCE, 128 bits at a time, through a sliding window of two 8-column sets: while the
+                // chain of chunk k runs (8 dependent DADDs, then four 128-bit stores) the set after next is in flight
+                // and the differences of chunk k+1 are formed from the two sets in registers.
+                // positions 8k .. 8k+7 = set k; d_k[u] = pos[8k + u + 5] - pos[8k + u] needs sets k and k+1
+#define FDN_LOADSET(W, kk)                                                        \
+    { W[0] = l2[4 * (kk)]; W[1] = l2[4 * (kk) + 1]; W[2] = l2[4 * (kk) + 2]; W[3] = l2[4 * (kk) + 3]; }
+#define FDN_DIFFS(D, W0, W1)                                                       \
+    {                                                                              \
+        D[0] = __dsub_rn(W0[2].y, W0[0].x); D[1] = __dsub_rn(W0[3].x, W0[0].y);    \
+        D[2] = __dsub_rn(W0[3].y, W0[1].x); D[3] = __dsub_rn(W1[0].x, W0[1].y);    \
+        D[4] = __dsub_rn(W1[0].y, W0[2].x); D[5] = __dsub_rn(W1[1].x, W0[2].y);    \
+        D[6] = __dsub_rn(W1[1].y, W0[3].x); D[7] = __dsub_rn(W1[2].x, W0[3].y);    \
+    }
+#define FDN_CHAIN8(D, kk)                                                          \
+    {                                                                              \
+        double2 s0, s1, s2, s3;                                                    \
+        S = __dadd_rn(S, D[0]); s0.x = S; S = __dadd_rn(S, D[1]); s0.y = S;        \
+        S = __dadd_rn(S, D[2]); s1.x = S; S = __dadd_rn(S, D[3]); s1.y = S;        \
+        S = __dadd_rn(S, D[4]); s2.x = S; S = __dadd_rn(S, D[5]); s2.y = S;        \
+        S = __dadd_rn(S, D[6]); s3.x = S; S = __dadd_rn(S, D[7]); s3.y = S;        \
+        l2[4 * (kk)] = s0; l2[4 * (kk) + 1] = s1; l2[4 * (kk) + 2] = s2; l2[4 * (kk) + 3] = s3; \
+    }
+                const int n8 = ncols >> 3;   // full chunks; ncols % 8 is 0 or 4
+                double2 wa_[4], wb_[4];
+                double d[8];
+                FDN_LOADSET(wa_, 0);
+                FDN_LOADSET(wb_, 1);   // (a line has LS >= ncols + 2m + 1 + 8 readable positions)
                 double S;
                 if (k == 0) {
                     // g = vsum[0]*(m+2) + vsum[1] + ... + vsum[m-1]   (columns clamp to the replicated border)
@@ -608,30 +625,40 @@ k_flow_iter_ws(WsArgs wa)
                 }
                 __syncwarp(hmask);   // the lanes leave their polling loops one by one: scan in lockstep from here on
                 if (!(wa.exp & 1)) {
-                    int i = 0, c8 = 0;
-                    while (c8 < n8) {
-                        if (c8 + 1 < n8) FDN_DIFF8(db, i + HC);
-                        FDN_CHAIN8(da, i);
-                        i += HC;
-                        if (++c8 == n8) break;
-                        if (c8 + 1 < n8) FDN_DIFF8(da, i + HC);
-                        FDN_CHAIN8(db, i);
-                        i += HC;
-                        ++c8;
-                        if ((i & 31) == 0) {   // every 32 columns: let the solve warps follow
+                    FDN_DIFFS(d, wa_, wb_);
+                    int kk = 0;
+                    while (kk < n8) {
+                        // sets: wa_ = kk, wb_ = kk+1; d = differences of chunk kk
+                        FDN_LOADSET(wa_, kk + 2);
+                        FDN_CHAIN8(d, kk);
+                        FDN_DIFFS(d, wb_, wa_);
+                        ++kk;
+                        if ((kk & 3) == 0) {   // every 32 columns: let the solve warps follow
                             __syncwarp(hmask);
                             __threadfence_block();
-                            if (lane == 0) prog[j & 1] = j * 4096 + i;
+                            if (lane == 0) prog[j & 1] = j * 4096 + 8 * kk;
+                        }
+                        if (kk == n8) break;
+                        // sets: wb_ = kk, wa_ = kk+1
+                        FDN_LOADSET(wb_, kk + 2);
+                        FDN_CHAIN8(d, kk);
+                        FDN_DIFFS(d, wa_, wb_);
+                        ++kk;
+                        if ((kk & 3) == 0) {
+                            __syncwarp(hmask);
+                            __threadfence_block();
+                            if (lane == 0) prog[j & 1] = j * 4096 + 8 * kk;
                         }
                     }
-                    if (HC == 8 && (ncols & 4)) {
-#pragma unroll
-                        for (int u = 0; u < 4; u++) da[u] = __dsub_rn(line[i + u + off], line[i + u]);
-#pragma unroll
-                        for (int u = 0; u < 4; u++) { S = __dadd_rn(S, da[u]); line[i + u] = S; }
+                    if (ncols & 4) {   // d[0..3] are the differences of the last 4 columns
+                        double2 s0, s1;
+                        S = __dadd_rn(S, d[0]); s0.x = S; S = __dadd_rn(S, d[1]); s0.y = S;
+                        S = __dadd_rn(S, d[2]); s1.x = S; S = __dadd_rn(S, d[3]); s1.y = S;
+                        l2[4 * n8] = s0; l2[4 * n8 + 1] = s1;
                     }
                 }
-#undef FDN_DIFF8
+#undef FDN_LOADSET
+#undef FDN_DIFFS
 #undef FDN_CHAIN8
                 if (k + 1 < a.strips) {
                     ulonglong2 o;
@@ -649,7 +676,7 @@ k_flow_iter_ws(WsArgs wa)
     }
 
     // =============================== column warps: phases V and S ===============================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 184;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
     // phase V: thread t <-> tile position t <-> image column x0 - m - 1 + t (clamped: replicated border); threads
     // beyond the strip's halo work on a clamped column too, their results are never read
     const int xcl = min(max(x0 - m - 1 + t, 0), w - 1);
