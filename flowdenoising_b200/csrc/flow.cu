@@ -562,6 +562,8 @@ k_flow_iter_ws(WsArgs wa)
                         }
                     }
                 }
+                // a solve warp without a chunk in this strip (narrow strips) must not run ahead of the tile either
+                while (prog[j & 1] < j * 4096 + ncols) __nanosleep(20);
                 nbar_arrive(BAR_FREE + (j & 1), NS + NT);     // the tile may be overwritten by phase V of tile j+2
             }
             return;

@@ -104,7 +104,7 @@ def test_polyexp_bit_exact(eng, shape, poly):
         assert np.array_equal(got[i], ref), f"max|d|={np.abs(got[i] - ref).max()}"
 
 
-@pytest.mark.parametrize("shape", SHAPES + [(40, 300), (9, 520)])
+@pytest.mark.parametrize("shape", SHAPES + [(40, 300), (9, 520), (64, 64), (33, 128), (17, 96), (70, 244)])
 @pytest.mark.parametrize("win", [5, 9, 15])
 def test_flow_iteration(eng, shape, win):
     """Stage 3: UpdateMatrices + box blur + solve, both running sums reproduced exactly -> bit-exact."""
