@@ -358,20 +358,23 @@ k_flow_iter(FlowIterArgs a)
 // ------------------------------------------------------------------------------------------------
 // k_flow_iter_ws: the same march as k_flow_iter, rebuilt as a warp-specialised pipeline (default for winsize 5).
 //   * 256 threads = two warpgroups. The "column" warpgroup (128 threads: one strip of CW <= 120 core columns plus
-//     its (m+1 | m) halo columns, thread t <-> image column x0 - m - 1 + t) runs phases V and S; one warp of the
-//     "scan" warpgroup runs phase H. The column sums of a tile go into one of TWO shared-memory tiles, so the scan of
-//     tile j overlaps phase V of tile j+1 and phase S of tile j-1. Registers are moved between the warpgroups with
-//     setmaxnreg (168 per column thread, 88 per scan thread, 2 blocks per SM);
+//     its (m+1 | m) halo columns, thread t <-> image column x0 - m - 1 + t) runs phase V only. In the second
+//     warpgroup one "scan" warp runs phase H and three "solve" warps run phase S. The column sums of a tile go into
+//     one of TWO shared-memory tiles, so the scan / solve of tile j overlap phase V of tiles j+1 and j+2. Registers
+//     are moved between the warpgroups with setmaxnreg (176 per column thread, 80 per scan / solve thread, 2 blocks
+//     per SM); hand-offs are named barriers (bar.arrive / bar.sync) and two progress counters in shared memory;
 //   * the ring of the last 2m+2 rows of M lives in REGISTERS: a tile is one ring period (TR = 2m+2 rows), so every
 //     ring slot is a compile-time constant of the unrolled row loop;
 //   * phase V is branch-free (selects, clamped gather addresses): the m+1 rows of half a tile form one straight-line
 //     block whose dependency chains the compiler interleaves. The bilinear gather reads R1 through L1 -- the
-//     kernel's shared memory is small (62 KB per block), so about 100 KB of L1 remain per SM and the rows of R1 a strip
-//     walks over stay resident; R0 / flow rows are streamed (evict-first) and register-prefetched one tile ahead;
+//     kernel's shared memory is small (62 KB per block), so about 100 KB of L1 remain per SM; every gather also
+//     prefetches (prefetch.global.L1) the R1 line the same column will need FDN_WS_PF rows further down, and the
+//     R0 / flow rows, read once, bypass L1 (ld.global.nc.L1::no_allocate) and are register-prefetched a tile ahead;
 //   * carries between strips travel as self-validating packets {32 data bits, 32-bit launch tag} (two per double,
 //     one 16-byte store): no fences, no flag, only the 5*TR scanning lanes ever wait for the left strip;
-//   * phase H keeps the differences of the next 8 columns in registers, so its serial part is the dependent DADD;
-//   * phase S runs a full tile as one straight-line block.
+//   * phase H reads a line once, 128 bits at a time, through a sliding register window, forms the differences of
+//     the next 8 columns while the dependent DADD chain of the current 8 runs, and stores 128 bits at a time;
+//   * phase S follows the scan through the tile in chunks of 32 columns (a full tile is one straight-line block).
 // Same arithmetic, same order of operations, same bits as k_flow_iter. Needs w % 4 == 0.
 // ------------------------------------------------------------------------------------------------
 struct RowIn {
@@ -467,6 +470,9 @@ __device__ __forceinline__ void ws_matrices_px(const RowIn& in, const Taps& tp, 
     M[4] = __fadd_rn(__fmul_rn(r6, r2), __fmul_rn(r5, r3));
 }
 
+#ifndef FDN_WS_POLL_NS
+#define FDN_WS_POLL_NS 200   // the solve warps have slack: poll the scan's progress coarsely, leave the issue slots to phase V
+#endif
 #ifndef FDN_WS_HC
 #define FDN_WS_HC 8
 #endif
@@ -496,7 +502,7 @@ __device__ __forceinline__ void nbar_arrive(int id, int count)
 //   column warps:  V(j) -> arrive FULL[j&1] -> wait DONE[(j-1)&1] -> S(j-1) -> barrier among column warps -> V(j+1) ...
 //   scan warp:     wait FULL[j&1] -> H(j) in place -> arrive DONE[j&1] -> ...
 // Registers: the kernel is compiled for (65536 / 2 blocks / 256 threads) = 128 per thread; the column warpgroup then
-// takes 168 (setmaxnreg.inc) and the scan warpgroup keeps 88 (setmaxnreg.dec).
+// takes 176 (setmaxnreg.inc) and the scan warpgroup keeps 80 (setmaxnreg.dec).
 template <int MT, int NT_>
 __global__ void __launch_bounds__(NT_ + 128, 2)
 k_flow_iter_ws(WsArgs wa)
@@ -522,7 +528,7 @@ k_flow_iter_ws(WsArgs wa)
 
     if (t >= NT) {
         // =============================== scan warp: phase H ===============================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
         if (t >= NT + 32) {
             // =============================== solve warps: phase S ===============================
             // regularised 2x2 solve in float64, flow written once. Full tiles run as one straight-line block (the
@@ -548,7 +554,7 @@ k_flow_iter_ws(WsArgs wa)
                 // scan warp has published that many columns
                 for (int q = sw; q * 32 < ncols; q += NS / 32) {
                     const int need = j * 4096 + min(q * 32 + 32, ncols);
-                    while (prog[j & 1] < need) __nanosleep(20);
+                    while (prog[j & 1] < need) __nanosleep(FDN_WS_POLL_NS);
                     __threadfence_block();
                     const int col = q * 32 + sln;
                     if (col < ncols && !(wa.exp & 8)) {
@@ -563,7 +569,7 @@ k_flow_iter_ws(WsArgs wa)
                     }
                 }
                 // a solve warp without a chunk in this strip (narrow strips) must not run ahead of the tile either
-                while (prog[j & 1] < j * 4096 + ncols) __nanosleep(20);
+                while (prog[j & 1] < j * 4096 + ncols) __nanosleep(FDN_WS_POLL_NS);
                 nbar_arrive(BAR_FREE + (j & 1), NS + NT);     // the tile may be overwritten by phase V of tile j+2
             }
             return;
@@ -678,7 +684,7 @@ k_flow_iter_ws(WsArgs wa)
     }
 
     // =============================== column warps: phases V and S ===============================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 176;");
     // phase V: thread t <-> tile position t <-> image column x0 - m - 1 + t (clamped: replicated border); threads
     // beyond the strip's halo work on a clamped column too, their results are never read
     const int xcl = min(max(x0 - m - 1 + t, 0), w - 1);
