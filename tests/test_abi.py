@@ -62,4 +62,6 @@ def test_workspace_grows_with_chunk():
     # + the carries/flags of the exact horizontal running sum (2 strips of 128 columns per image)
     R = 64 * 5 * (256 * 256 + 128 * 128 + 64 * 64 + 32 * 32) * 4
     carries = 64 * 2 * 256 * 5 * 8 + 64 * 64 * 8
-    assert b == R + 3 * (64 * 256 * 256 * 2 * 4) + carries
+    # + the carry packets of the warp-specialised kernel (3 strips of <= 120 columns, 16 bytes per carry)
+    packets = 64 * 3 * 256 * 5 * 16
+    assert b == R + 3 * (64 * 256 * 256 * 2 * 4) + carries + packets
