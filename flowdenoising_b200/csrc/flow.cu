@@ -483,7 +483,7 @@ __device__ __forceinline__ void ws_matrices_px(const RowIn& in, const Taps& tp, 
 struct WsArgs {
     FlowIterArgs a;
     int CW;
-    int exp;               // timing experiments (FDN_EXP), results are wrong when != 0
+    int exp;               // 0 in product builds; phase-removal timing experiments with -DFDN_WS_EXPERIMENTS (FDN_EXP)
     unsigned tag;          // launch tag of the carry packets (never 0)
     ulonglong2* packets;   // [n][strips][h][5]: {lo32 | tag << 32, hi32 | tag << 32}
 };
@@ -895,7 +895,10 @@ int launch_flow_iter(const float* R, int64_t R_stride, SlotMap map0, SlotMap map
         }
         if ((unsigned)g_flow_epoch == 0) g_flow_epoch++;   // the packet tag is the low word of the epoch, never 0
         wa.tag = (unsigned)g_flow_epoch;
+        wa.exp = 0;
+#ifdef FDN_WS_EXPERIMENTS   // phase-removal timing experiments of tools/flow_iter_lab.py (FDN_EXP bit mask): wrong results
         { const char* e = getenv("FDN_EXP"); wa.exp = e ? atoi(e) : 0; }
+#endif
         for (int b0 = 0; b0 < n; b0 += 65535) {
             const int nb = n - b0 < 65535 ? n - b0 : 65535;
             a.map0 = map0; a.map0.base += b0;
@@ -1149,9 +1152,61 @@ k_flow_upsample2(const float2* __restrict__ in, int hin, int win, float4* __rest
     out[(((int64_t)b * h + dy) * w + dx) / 2] = make_float4(o0.x, o0.y, o1.x, o1.y);
 }
 
+// Exact factor 2 in both directions (every level of an even-sized pyramid): the source coordinate of output 2k is
+// k - 0.25 and of 2k+1 is k + 0.25, so floor / fraction are constants (fraction 0.75 and 0.25, exact in float32) and the
+// float64 coordinate arithmetic of k_flow_upsample2 folds away; the interpolation itself is the same sequence of
+// float32 operations. One thread = outputs (2k, 2k+1) of one row from source columns k-1, k, k+1.
+__global__ void __launch_bounds__(128)
+k_flow_upsample_x2(const float2* __restrict__ in, int hin, int win, float4* __restrict__ out, int h, int w)
+{
+    const int k = blockIdx.x * 128 + threadIdx.x;   // source column
+    const int dy = blockIdx.y;
+    const int b = blockIdx.z;
+    if (k >= win) return;
+    // rows: dy = 2j -> sy = j - 1, fy = 0.75; dy = 2j + 1 -> sy = j, fy = 0.25 (no clamping of the fraction vertically)
+    const int j = dy >> 1;
+    const int sy = (dy & 1) ? j : j - 1;
+    const float b1 = (dy & 1) ? 0.25f : 0.75f, b0 = __fsub_rn(1.f, b1);
+    const int sy0 = min(max(sy, 0), hin - 1), sy1 = min(max(sy + 1, 0), hin - 1);
+    const float2* S0 = in + ((int64_t)b * hin + sy0) * win;
+    const float2* S1 = in + ((int64_t)b * hin + sy1) * win;
+    const int km = max(k - 1, 0), kp = min(k + 1, win - 1);
+    const float2 u0 = __ldg(S0 + km), u1 = __ldg(S0 + k), u2 = __ldg(S0 + kp);
+    const float2 v0 = __ldg(S1 + km), v1 = __ldg(S1 + k), v2 = __ldg(S1 + kp);
+    // output 2k: sx = k - 1, fx = 0.75 (sx < 0 -> sx = 0, fx = 0; sx >= win - 1 cannot happen for k - 1)
+    float a1 = k >= 1 ? 0.75f : 0.f, a0 = __fsub_rn(1.f, a1);
+    float2 p0 = k >= 1 ? u0 : u1, p1 = k >= 1 ? u1 : (win > 1 ? u2 : u1);
+    float2 q0 = k >= 1 ? v0 : v1, q1 = k >= 1 ? v1 : (win > 1 ? v2 : v1);
+    float r0x = __fadd_rn(__fmul_rn(p0.x, a0), __fmul_rn(p1.x, a1)), r0y = __fadd_rn(__fmul_rn(p0.y, a0), __fmul_rn(p1.y, a1));
+    float r1x = __fadd_rn(__fmul_rn(q0.x, a0), __fmul_rn(q1.x, a1)), r1y = __fadd_rn(__fmul_rn(q0.y, a0), __fmul_rn(q1.y, a1));
+    float4 o;
+    o.x = __fmul_rn(__fadd_rn(__fmul_rn(r0x, b0), __fmul_rn(r1x, b1)), 2.f);
+    o.y = __fmul_rn(__fadd_rn(__fmul_rn(r0y, b0), __fmul_rn(r1y, b1)), 2.f);
+    // output 2k + 1: sx = k, fx = 0.25 (sx >= win - 1 -> sx = win - 1, fx = 0)
+    const bool last = k >= win - 1;
+    a1 = last ? 0.f : 0.25f; a0 = __fsub_rn(1.f, a1);
+    p0 = u1; p1 = u2; q0 = v1; q1 = v2;   // for the last column u2 == u1 (kp is clamped)
+    r0x = __fadd_rn(__fmul_rn(p0.x, a0), __fmul_rn(p1.x, a1)); r0y = __fadd_rn(__fmul_rn(p0.y, a0), __fmul_rn(p1.y, a1));
+    r1x = __fadd_rn(__fmul_rn(q0.x, a0), __fmul_rn(q1.x, a1)); r1y = __fadd_rn(__fmul_rn(q0.y, a0), __fmul_rn(q1.y, a1));
+    o.z = __fmul_rn(__fadd_rn(__fmul_rn(r0x, b0), __fmul_rn(r1x, b1)), 2.f);
+    o.w = __fmul_rn(__fadd_rn(__fmul_rn(r0y, b0), __fmul_rn(r1y, b1)), 2.f);
+    out[(((int64_t)b * h + dy) * w) / 2 + k] = o;
+}
+
 int launch_flow_upsample(const float* flow, int n, int hin, int win, float* out, int h, int w, cudaStream_t st)
 {
     const double scale_x = 1. / ((double)w / win), scale_y = 1. / ((double)h / hin);
+    if (w == 2 * win && h == 2 * hin && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+        for (int b0 = 0; b0 < n; b0 += 65535) {
+            const int nb = n - b0 < 65535 ? n - b0 : 65535;
+            dim3 grid((unsigned)cdiv(win, 128), (unsigned)h, (unsigned)nb);
+            ProfScope ps(K_FLOW_UP, 8.0 * nb * ((double)hin * win + (double)h * w), st);
+            k_flow_upsample_x2<<<grid, 128, 0, st>>>(reinterpret_cast<const float2*>(flow) + (int64_t)b0 * hin * win, hin, win,
+                                                     reinterpret_cast<float4*>(out + (int64_t)b0 * h * w * 2), h, w);
+            FDN_LAUNCHED("k_flow_upsample_x2");
+        }
+        return FDN_OK;
+    }
     if (w % 2 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
         for (int b0 = 0; b0 < n; b0 += 65535) {
             const int nb = n - b0 < 65535 ? n - b0 : 65535;

@@ -131,6 +131,36 @@ def test_flow_iteration(eng, shape, win):
         assert np.array_equal(got[i], ref), f"max|d|={d.max()} bit-equal fraction {np.mean(got[i] == ref)}"
 
 
+@pytest.mark.parametrize("shape,scale", [((96, 256), 1.0), ((130, 372), 6.0), ((64, 64), 3.0)])
+def test_flow_iteration_kernels_agree(eng, shape, scale, monkeypatch):
+    """The warp-specialised kernel (k_flow_iter_ws, default for winsize 5) and the strip kernel (k_flow_iter, pinned
+    against the oracle above) write the same bits, also for flows of many pixels (gathers far from the identity
+    position, out-of-image lookups) and over several chained launches that reuse the scratch without clearing it."""
+    n = 5
+    h, w = shape
+    imgs = images(shape, n + 1, 21)
+    R = np.stack([O.polyexp(imgs[i]) for i in range(n + 1)])
+    rng = np.random.default_rng(22)
+    flow = (rng.standard_normal((n, h, w, 2)) * scale).astype(np.float32)
+    flow[1, :, : w // 2] += 7.5        # a coherent drift on half an image
+    flow[2, 5:9, 10:40] = 1e4          # far outside the image
+    dR = dev(R_from_oracle_layout(R))
+    nscr = eng.lib.fdn_flow_iteration_scratch_bytes(n, h, w)
+    scr = torch.zeros(nscr, dtype=torch.uint8, device="cuda")
+    res = {}
+    for variant in ("old", "ws"):
+        monkeypatch.setenv("FDN_FLOW_ITER", variant)
+        cur = dev(flow)
+        for it in range(3):            # chained, like the iterations of a level
+            out = torch.empty_like(cur)
+            rc = eng.lib.fdn_flow_iteration(dR[:n].data_ptr(), dR[1:].data_ptr(), cur.data_ptr(), out.data_ptr(), n, h, w,
+                                            5, scr.data_ptr(), nscr, None)
+            assert rc == 0, eng.lib.fdn_last_error()
+            cur = out
+        res[variant] = cur.cpu().numpy()
+    assert np.array_equal(res["old"].view(np.int32), res["ws"].view(np.int32))
+
+
 def test_flow_resampling_bit_exact(eng):
     rng = np.random.default_rng(6)
     n = 2

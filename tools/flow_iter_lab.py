@@ -1,5 +1,5 @@
 """Development harness for the flow-iteration kernel (stage 3): times one launch shape in isolation on realistic
-inputs and checks that the windowed kernel (k_flow_iter_win) and the strip kernel (k_flow_iter, already pinned
+inputs and checks that the warp-specialised kernel (k_flow_iter_ws) and the strip kernel (k_flow_iter, already pinned
 against the oracle) write identical bits.
 
     python tools/flow_iter_lab.py [--n 128] [--h 1024] [--w 1024] [--win 5] [--reps 10] [--iters 3]
@@ -7,7 +7,12 @@ against the oracle) write identical bits.
 Inputs: n+1 slices of the bench's synthetic volume -> polynomial expansions (fdn_polyexp); pair b = (slice b, b+1).
 The flow fed to the timed launch is the result of `iters - 1` earlier iterations from a zero flow (what the
 level-0 launches of a pass see when the coarser levels found nothing), optionally scaled (--flow-scale) to
-stress the out-of-window fallback.
+stress gathers far from the identity position.
+
+Phase-removal experiments (which phase is the critical path?): build with
+    FDN_NVCC_EXTRA=-DFDN_WS_EXPERIMENTS python -m flowdenoising_b200._build
+and run with FDN_EXP=<bit mask> (1: no scan chain, 2: no packet wait, 4: no column-sum update, 8: no solve). Results are
+wrong with any bit set; the product build ignores FDN_EXP.
 """
 import argparse
 import hashlib
