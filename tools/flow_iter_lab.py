@@ -34,7 +34,7 @@ def main():
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--flow-scale", type=float, default=1.0)
     ap.add_argument("--delta", type=int, default=1, help="slice distance of a pair")
-    ap.add_argument("--only", default=None, help="old | win: skip the comparison")
+    ap.add_argument("--only", default=None, help="old | ws: skip the comparison")
     a = ap.parse_args()
 
     import torch
@@ -72,7 +72,7 @@ def main():
           f"max {mag.max().item():.2f}")
 
     outs = {}
-    for variant in (["old", "win"] if a.only is None else [a.only]):
+    for variant in (["old", "ws"] if a.only is None else [a.only]):
         out = torch.empty_like(f0)
         run(variant, f0, out)
         run(variant, f0, out)
@@ -90,12 +90,12 @@ def main():
               f"({gb / med * 1e3 / 6545.9:.3f} of the measured HBM peak)")
         outs[variant] = out
     if len(outs) == 2:
-        same = torch.equal(outs["old"].view(torch.int32), outs["win"].view(torch.int32))
-        nd = (outs["old"].view(torch.int32) != outs["win"].view(torch.int32)).sum().item()
+        same = torch.equal(outs["old"].view(torch.int32), outs["ws"].view(torch.int32))
+        nd = (outs["old"].view(torch.int32) != outs["ws"].view(torch.int32)).sum().item()
         print("bit-identical:", same, "differing words:", nd)
         if not same:
-            d = (outs["old"] - outs["win"]).abs()
-            idx = torch.nonzero(outs["old"].view(torch.int32) != outs["win"].view(torch.int32))[:5]
+            d = (outs["old"] - outs["ws"]).abs()
+            idx = torch.nonzero(outs["old"].view(torch.int32) != outs["ws"].view(torch.int32))[:5]
             print("max|d|", d.max().item(), "first diffs at", idx.tolist())
             sys.exit(1)
 
