@@ -333,7 +333,10 @@ def main():
                     "avg_launch_ms": kd["ms"] / kd["launches"], "launches": kd["launches"],
                     "algorithmic_bytes_per_launch": kd["bytes"] / kd["launches"],
                     "share_of_step": kd["ms"] / (ms_total if ms_total > 0 else 1.0),
-                    "kernel_ms_per_step": {k: round(v["ms"] / args.steps, 3) for k, v in sorted(kern.items())}}
+                    "kernel_ms_per_step": {k: round(v["ms"] / args.steps, 3) for k, v in sorted(kern.items())},
+                    # every kernel of the path against the same peak (algorithmic bytes / CUDA-event time)
+                    "kernel_frac_of_peak": {k: round(v["bytes"] / (v["ms"] * 1e-3) / 1e9 / peak, 3)
+                                            for k, v in sorted(kern.items()) if v["ms"] > 0}}
     model_b = 24.0 if args.no_of else MODEL_BYTES_PER_VOXEL_CFG2 * (1.0 if shape == (512, 1024, 1024) else float("nan"))
     whole_job_frac = (model_b * nvox / (ms_step * 1e-3) / 1e9) / (world * peak) if model_b == model_b else None
 

@@ -799,13 +799,13 @@ static unsigned long long g_flow_epoch = 1;
 static int strip_width(int w) { return w > 96 ? 128 : 32; }   // k_flow_iter
 
 // strips of k_flow_iter_ws: CW = multiple of 4, <= WsCfg::CWMAX
-static int win_strip_width(int w, int cwmax)
+static int ws_strip_width(int w, int cwmax)
 {
     const int strips = (int)cdiv(w, cwmax);
     return (int)((cdiv(w, strips) + 3) / 4 * 4);
 }
-#define FDN_WIN_NT 128
-typedef WsCfg<2, FDN_WIN_NT> WinCfg2;
+#define FDN_WS_NT 128
+typedef WsCfg<2, FDN_WS_NT> WsCfg2;
 
 static size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 static size_t flow_flag_bytes(int n) { return align256(sizeof(unsigned long long) * (size_t)n * FDN_MAX_STRIPS); }
@@ -815,7 +815,7 @@ static size_t flow_carry_bytes(int n, int h, int w)   // k_flow_iter: one double
 }
 static size_t flow_packet_bytes(int n, int h, int w)  // k_flow_iter_ws: one 16-byte packet pair per carry
 {
-    const size_t strips = (size_t)cdiv(w, win_strip_width(w, WinCfg2::CWMAX));
+    const size_t strips = (size_t)cdiv(w, ws_strip_width(w, WsCfg2::CWMAX));
     return align256(sizeof(ulonglong2) * 5 * (size_t)n * strips * h);
 }
 
@@ -884,23 +884,23 @@ int launch_flow_iter(const float* R, int64_t R_stride, SlotMap map0, SlotMap map
                      (reinterpret_cast<uintptr_t>(R) & 15) == 0 && R_stride % 4 == 0;
     if (win) {
         WsArgs wa;
-        wa.CW = win_strip_width(w, WinCfg2::CWMAX);
+        wa.CW = ws_strip_width(w, WsCfg2::CWMAX);
         a.strips = (int)cdiv(w, wa.CW);
         FDN_CHECK_ARG(a.strips <= FDN_MAX_STRIPS, "image too wide (%d strips)", a.strips);
         wa.packets = reinterpret_cast<ulonglong2*>(static_cast<char*>(scratch) + flow_flag_bytes(n));
         static bool attr_set = false;
         if (!attr_set) {
-            FDN_CUDA(cudaFuncSetAttribute(k_flow_iter_ws<2, FDN_WIN_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)WinCfg2::smem_bytes));
+            FDN_CUDA(cudaFuncSetAttribute(k_flow_iter_ws<2, FDN_WS_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)WsCfg2::smem_bytes));
             // leave the rest of the SM's L1/shared array to L1: the R1 rows a strip walks over live there
-            FDN_CUDA(cudaFuncSetAttribute(k_flow_iter_ws<2, FDN_WIN_NT>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                          (int)((2 * (WinCfg2::smem_bytes + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024))));
+            FDN_CUDA(cudaFuncSetAttribute(k_flow_iter_ws<2, FDN_WS_NT>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                          (int)((2 * (WsCfg2::smem_bytes + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024))));
             if (getenv("FDN_DEBUG")) {
                 int nb = 0;
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_flow_iter_ws<2, FDN_WIN_NT>, FDN_WIN_NT + 128,
-                                                              WinCfg2::smem_bytes);
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_flow_iter_ws<2, FDN_WS_NT>, FDN_WS_NT + 128,
+                                                              WsCfg2::smem_bytes);
                 fprintf(stderr, "[fdn] k_flow_iter_ws: %d blocks/SM, %zu B shared memory per block\n", nb,
-                        (size_t)WinCfg2::smem_bytes);
+                        (size_t)WsCfg2::smem_bytes);
             }
             attr_set = true;
         }
@@ -920,7 +920,7 @@ int launch_flow_iter(const float* R, int64_t R_stride, SlotMap map0, SlotMap map
             wa.a = a;
             ProfScope ps(K_FLOW_ITER, 56.0 * nb * h * w, st);
             dim3 grid((unsigned)a.strips, (unsigned)nb);
-            k_flow_iter_ws<2, FDN_WIN_NT><<<grid, FDN_WIN_NT + 128, WinCfg2::smem_bytes, st>>>(wa);
+            k_flow_iter_ws<2, FDN_WS_NT><<<grid, FDN_WS_NT + 128, WsCfg2::smem_bytes, st>>>(wa);
             FDN_LAUNCHED("k_flow_iter_ws");
             wa.packets += (int64_t)nb * a.strips * h * 5;
         }
