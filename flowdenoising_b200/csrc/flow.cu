@@ -392,7 +392,7 @@ struct WsCfg {
     static constexpr int CWMAX = (NT - HALO) & ~3;
     static constexpr int LS = NT + 2;       // tile line stride in doubles (even: every line is 16-byte aligned)
     static constexpr size_t tiles_bytes = 2 * sizeof(double) * TR * 5 * LS + 128;   // two tiles (+ the scan's read-ahead past the last line)
-    static constexpr size_t smem_bytes = tiles_bytes + 16;                    // + the scan's progress counters
+    static constexpr size_t smem_bytes = tiles_bytes + 16;                    // + the scan's progress counters, the ticket
     static_assert(5 * TR <= 32, "phase H runs in one warp");
 };
 
@@ -493,6 +493,7 @@ struct WsArgs {
     int exp;               // 0 in product builds; phase-removal timing experiments with -DFDN_WS_EXPERIMENTS (FDN_EXP)
     unsigned tag;          // launch tag of the carry packets (never 0)
     ulonglong2* packets;   // [n][strips][h][5]: {lo32 | tag << 32, hi32 | tag << 32}
+    unsigned* ticket;      // [2]: tickets taken, blocks that have taken one (both 0 between launches)
 };
 
 // named barriers (id 0 is __syncthreads)
@@ -523,15 +524,28 @@ k_flow_iter_ws(WsArgs wa)
     volatile int* prog = reinterpret_cast<volatile int*>(smem_ws + C::tiles_bytes);   // [2]: j * 4096 + columns scanned
     const int h = a.h, w = a.w;
     const int t = threadIdx.x;
-    const int k = blockIdx.x;  // strip
-    const int b = blockIdx.y;  // image pair
+    // Which (pair, strip) this block works on is decided by a ticket, not by blockIdx: a strip waits for the strip to
+    // its left, so the left strip must already be running. Tickets are handed out in the order blocks actually start
+    // (strip index fastest), whatever order the hardware dispatches them in. The block that takes the last ticket
+    // re-arms both counters for the next launch on the stream.
+    if (t == 0) {
+        const unsigned total = gridDim.x * gridDim.y;
+        const unsigned tk = atomicAdd(wa.ticket, 1u);
+        prog[2] = (int)tk;
+        if (atomicAdd(wa.ticket + 1, 1u) == total - 1) {   // every ticket has been taken
+            wa.ticket[0] = 0;
+            wa.ticket[1] = 0;
+        }
+    }
+    if (t < 2) prog[t] = -1;
+    __syncthreads();
+    const int ticket = prog[2];
+    const int k = ticket % (int)gridDim.x;  // strip
+    const int b = ticket / (int)gridDim.x;  // image pair
     const int CW = wa.CW;
     const int x0 = k * CW;
     const int ncols = min(CW, w - x0);   // multiple of 4
     const int ntiles = (h + TR - 1) / TR;
-
-    if (t < 2) prog[t] = -1;
-    __syncthreads();
 
     if (t >= NT) {
         // =============================== scan warp: phase H ===============================
@@ -809,6 +823,7 @@ typedef WsCfg<2, FDN_WS_NT> WsCfg2;
 
 static size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 static size_t flow_flag_bytes(int n) { return align256(sizeof(unsigned long long) * (size_t)n * FDN_MAX_STRIPS); }
+static const size_t kFlowTicketBytes = 256;   // k_flow_iter_ws: ticket counters
 static size_t flow_carry_bytes(int n, int h, int w)   // k_flow_iter: one double per (pair, strip, row, channel)
 {
     return align256(sizeof(double) * 5 * (size_t)n * (size_t)cdiv(w, strip_width(w)) * h);
@@ -819,7 +834,8 @@ static size_t flow_packet_bytes(int n, int h, int w)  // k_flow_iter_ws: one 16-
     return align256(sizeof(ulonglong2) * 5 * (size_t)n * strips * h);
 }
 
-// Scratch layout: [flags: n * MAX_STRIPS u64][packets of k_flow_iter_ws ...  ... carries of k_flow_iter]. The flag
+// Scratch layout: [flags: n * MAX_STRIPS u64][tickets of k_flow_iter_ws][packets of k_flow_iter_ws ...  ... carries of
+// k_flow_iter]. The flag
 // area has the same place and size for every pyramid level that shares the scratch (it only ever holds epochs of
 // earlier launches, which compare below the current one). Packets grow from the front and plain carries sit at the
 // END of the scratch, so a level run by one kernel never writes into the area the other kernel polls at another
@@ -827,7 +843,7 @@ static size_t flow_packet_bytes(int n, int h, int w)  // k_flow_iter_ws: one 16-
 // reads them.
 size_t flow_iter_scratch_bytes(int n, int h, int w)
 {
-    return flow_flag_bytes(n) + flow_packet_bytes(n, h, w) + flow_carry_bytes(n, h, w);
+    return flow_flag_bytes(n) + kFlowTicketBytes + flow_packet_bytes(n, h, w) + flow_carry_bytes(n, h, w);
 }
 
 int flow_iter_scratch_init(void* scratch, size_t bytes, cudaStream_t st)
@@ -887,7 +903,8 @@ int launch_flow_iter(const float* R, int64_t R_stride, SlotMap map0, SlotMap map
         wa.CW = ws_strip_width(w, WsCfg2::CWMAX);
         a.strips = (int)cdiv(w, wa.CW);
         FDN_CHECK_ARG(a.strips <= FDN_MAX_STRIPS, "image too wide (%d strips)", a.strips);
-        wa.packets = reinterpret_cast<ulonglong2*>(static_cast<char*>(scratch) + flow_flag_bytes(n));
+        wa.ticket = reinterpret_cast<unsigned*>(static_cast<char*>(scratch) + flow_flag_bytes(n));
+        wa.packets = reinterpret_cast<ulonglong2*>(static_cast<char*>(scratch) + flow_flag_bytes(n) + kFlowTicketBytes);
         static bool attr_set = false;
         if (!attr_set) {
             FDN_CUDA(cudaFuncSetAttribute(k_flow_iter_ws<2, FDN_WS_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,

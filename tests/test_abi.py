@@ -63,5 +63,5 @@ def test_workspace_grows_with_chunk():
     R = 64 * 5 * (256 * 256 + 128 * 128 + 64 * 64 + 32 * 32) * 4
     carries = 64 * 2 * 256 * 5 * 8 + 64 * 64 * 8
     # + the carry packets of the warp-specialised kernel (3 strips of <= 120 columns, 16 bytes per carry)
-    packets = 64 * 3 * 256 * 5 * 16
+    packets = 64 * 3 * 256 * 5 * 16 + 256     # + its ticket counters
     assert b == R + 3 * (64 * 256 * 256 * 2 * 4) + carries + packets
