@@ -1183,42 +1183,53 @@ k_flow_upsample2(const float2* __restrict__ in, int hin, int win, float4* __rest
 // Exact factor 2 in both directions (every level of an even-sized pyramid): the source coordinate of output 2k is
 // k - 0.25 and of 2k+1 is k + 0.25, so floor / fraction are constants (fraction 0.75 and 0.25, exact in float32) and the
 // float64 coordinate arithmetic of k_flow_upsample2 folds away; the interpolation itself is the same sequence of
-// float32 operations. One thread = outputs (2k, 2k+1) of one row from source columns k-1, k, k+1.
+// float32 operations. One thread = the 2 x 2 outputs (rows 2j, 2j+1, columns 2k, 2k+1) from the 3 x 3 source
+// neighbourhood of (j, k).
 __global__ void __launch_bounds__(128)
 k_flow_upsample_x2(const float2* __restrict__ in, int hin, int win, float4* __restrict__ out, int h, int w)
 {
     const int k = blockIdx.x * 128 + threadIdx.x;   // source column
-    const int dy = blockIdx.y;
+    const int j = blockIdx.y;                       // source row: output rows 2j and 2j + 1
     const int b = blockIdx.z;
     if (k >= win) return;
-    // rows: dy = 2j -> sy = j - 1, fy = 0.75; dy = 2j + 1 -> sy = j, fy = 0.25 (no clamping of the fraction vertically)
-    const int j = dy >> 1;
-    const int sy = (dy & 1) ? j : j - 1;
-    const float b1 = (dy & 1) ? 0.25f : 0.75f, b0 = __fsub_rn(1.f, b1);
-    const int sy0 = min(max(sy, 0), hin - 1), sy1 = min(max(sy + 1, 0), hin - 1);
-    const float2* S0 = in + ((int64_t)b * hin + sy0) * win;
-    const float2* S1 = in + ((int64_t)b * hin + sy1) * win;
+    // rows: dy = 2j -> sy = j - 1, fy = 0.75; dy = 2j + 1 -> sy = j, fy = 0.25 (no clamping of the fraction vertically,
+    // the row indices are clamped)
+    const float2* Sm = in + ((int64_t)b * hin + max(j - 1, 0)) * win;
+    const float2* Sc = in + ((int64_t)b * hin + j) * win;
+    const float2* Sp = in + ((int64_t)b * hin + min(j + 1, hin - 1)) * win;
     const int km = max(k - 1, 0), kp = min(k + 1, win - 1);
-    const float2 u0 = __ldg(S0 + km), u1 = __ldg(S0 + k), u2 = __ldg(S0 + kp);
-    const float2 v0 = __ldg(S1 + km), v1 = __ldg(S1 + k), v2 = __ldg(S1 + kp);
-    // output 2k: sx = k - 1, fx = 0.75 (sx < 0 -> sx = 0, fx = 0; sx >= win - 1 cannot happen for k - 1)
-    float a1 = k >= 1 ? 0.75f : 0.f, a0 = __fsub_rn(1.f, a1);
-    float2 p0 = k >= 1 ? u0 : u1, p1 = k >= 1 ? u1 : (win > 1 ? u2 : u1);
-    float2 q0 = k >= 1 ? v0 : v1, q1 = k >= 1 ? v1 : (win > 1 ? v2 : v1);
-    float r0x = __fadd_rn(__fmul_rn(p0.x, a0), __fmul_rn(p1.x, a1)), r0y = __fadd_rn(__fmul_rn(p0.y, a0), __fmul_rn(p1.y, a1));
-    float r1x = __fadd_rn(__fmul_rn(q0.x, a0), __fmul_rn(q1.x, a1)), r1y = __fadd_rn(__fmul_rn(q0.y, a0), __fmul_rn(q1.y, a1));
-    float4 o;
-    o.x = __fmul_rn(__fadd_rn(__fmul_rn(r0x, b0), __fmul_rn(r1x, b1)), 2.f);
-    o.y = __fmul_rn(__fadd_rn(__fmul_rn(r0y, b0), __fmul_rn(r1y, b1)), 2.f);
-    // output 2k + 1: sx = k, fx = 0.25 (sx >= win - 1 -> sx = win - 1, fx = 0)
-    const bool last = k >= win - 1;
-    a1 = last ? 0.f : 0.25f; a0 = __fsub_rn(1.f, a1);
-    p0 = u1; p1 = u2; q0 = v1; q1 = v2;   // for the last column u2 == u1 (kp is clamped)
-    r0x = __fadd_rn(__fmul_rn(p0.x, a0), __fmul_rn(p1.x, a1)); r0y = __fadd_rn(__fmul_rn(p0.y, a0), __fmul_rn(p1.y, a1));
-    r1x = __fadd_rn(__fmul_rn(q0.x, a0), __fmul_rn(q1.x, a1)); r1y = __fadd_rn(__fmul_rn(q0.y, a0), __fmul_rn(q1.y, a1));
-    o.z = __fmul_rn(__fadd_rn(__fmul_rn(r0x, b0), __fmul_rn(r1x, b1)), 2.f);
-    o.w = __fmul_rn(__fadd_rn(__fmul_rn(r0y, b0), __fmul_rn(r1y, b1)), 2.f);
-    out[(((int64_t)b * h + dy) * w) / 2 + k] = o;
+    float2 v[3][3];
+    v[0][0] = __ldg(Sm + km); v[0][1] = __ldg(Sm + k); v[0][2] = __ldg(Sm + kp);
+    v[1][0] = __ldg(Sc + km); v[1][1] = __ldg(Sc + k); v[1][2] = __ldg(Sc + kp);
+    v[2][0] = __ldg(Sp + km); v[2][1] = __ldg(Sp + k); v[2][2] = __ldg(Sp + kp);
+    // columns: output 2k: sx = k - 1, fx = 0.75 (k = 0: sx = 0, fx = 0 -> taps S[0], S[min(1, win-1)]);
+    //          output 2k+1: sx = k, fx = 0.25 (k = win-1: fx = 0 -> taps S[win-1], S[win-1])
+    const float ea1 = k >= 1 ? 0.75f : 0.f, ea0 = __fsub_rn(1.f, ea1);
+    const float oa1 = k >= win - 1 ? 0.f : 0.25f, oa0 = __fsub_rn(1.f, oa1);
+    const int e0 = k >= 1 ? 0 : 1, e1 = k >= 1 ? 1 : 2;   // tap columns of the even output inside v[.][0..2]
+    float2 he[3], ho[3];   // horizontally interpolated rows (even / odd output column)
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        const float2 p0 = e0 == 0 ? v[r][0] : v[r][1], p1 = e1 == 1 ? v[r][1] : v[r][2];
+        he[r].x = __fadd_rn(__fmul_rn(p0.x, ea0), __fmul_rn(p1.x, ea1));
+        he[r].y = __fadd_rn(__fmul_rn(p0.y, ea0), __fmul_rn(p1.y, ea1));
+        ho[r].x = __fadd_rn(__fmul_rn(v[r][1].x, oa0), __fmul_rn(v[r][2].x, oa1));
+        ho[r].y = __fadd_rn(__fmul_rn(v[r][1].y, oa0), __fmul_rn(v[r][2].y, oa1));
+    }
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+        const int dy = 2 * j + half;
+        if (dy >= h) break;
+        // dy even: rows (j-1, j) with b1 = 0.75; dy odd: rows (j, j+1) with b1 = 0.25
+        const float b1 = half ? 0.25f : 0.75f, b0 = __fsub_rn(1.f, b1);
+        const float2 re0 = he[half], re1 = he[half + 1], ro0 = ho[half], ro1 = ho[half + 1];
+        float4 o;
+        o.x = __fmul_rn(__fadd_rn(__fmul_rn(re0.x, b0), __fmul_rn(re1.x, b1)), 2.f);
+        o.y = __fmul_rn(__fadd_rn(__fmul_rn(re0.y, b0), __fmul_rn(re1.y, b1)), 2.f);
+        o.z = __fmul_rn(__fadd_rn(__fmul_rn(ro0.x, b0), __fmul_rn(ro1.x, b1)), 2.f);
+        o.w = __fmul_rn(__fadd_rn(__fmul_rn(ro0.y, b0), __fmul_rn(ro1.y, b1)), 2.f);
+        out[(((int64_t)b * h + dy) * w) / 2 + k] = o;
+    }
 }
 
 int launch_flow_upsample(const float* flow, int n, int hin, int win, float* out, int h, int w, cudaStream_t st)
@@ -1227,7 +1238,7 @@ int launch_flow_upsample(const float* flow, int n, int hin, int win, float* out,
     if (w == 2 * win && h == 2 * hin && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
         for (int b0 = 0; b0 < n; b0 += 65535) {
             const int nb = n - b0 < 65535 ? n - b0 : 65535;
-            dim3 grid((unsigned)cdiv(win, 128), (unsigned)h, (unsigned)nb);
+            dim3 grid((unsigned)cdiv(win, 128), (unsigned)hin, (unsigned)nb);
             ProfScope ps(K_FLOW_UP, 8.0 * nb * ((double)hin * win + (double)h * w), st);
             k_flow_upsample_x2<<<grid, 128, 0, st>>>(reinterpret_cast<const float2*>(flow) + (int64_t)b0 * hin * win, hin, win,
                                                      reinterpret_cast<float4*>(out + (int64_t)b0 * h * w * 2), h, w);
