@@ -176,15 +176,100 @@ k_blur_cols(const float* __restrict__ in, float* __restrict__ out, int H, int W,
     out[((int64_t)b * H + y) * W + x] = acc;
 }
 
+// Register-window variants for the tap counts the Farneback pyramid actually uses (3, 7, 17 taps: half widths 1, 3,
+// 8). Same arithmetic per output as k_blur_rows / k_blur_cols; each thread produces 4 outputs from one window of
+// 4 + 2R inputs instead of 4 * (2R + 1) loads with their address arithmetic.
+template <int R>
+__global__ void __launch_bounds__(128)
+k_blur_rows4(const float* __restrict__ in, int64_t in_ss, int64_t in_rs, SlotMap in_map, float* __restrict__ out, int H,
+             int W, BlurTaps bt)
+{
+    constexpr int KS = 2 * R + 1;
+    const int x0 = (blockIdx.x * 128 + threadIdx.x) * 4;   // W % 4 == 0
+    const int y = blockIdx.y;
+    const int b = blockIdx.z;
+    if (x0 >= W) return;
+    const float* s = in + (int64_t)in_map.slot(b) * in_ss + (int64_t)y * in_rs;
+    float v[4 + 2 * R];
+    if (x0 >= R && x0 + 3 + R < W) {
+#pragma unroll
+        for (int i = 0; i < 4 + 2 * R; i++) v[i] = __ldg(s + x0 - R + i);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4 + 2 * R; i++) v[i] = __ldg(s + reflect101(x0 - R + i, W));
+    }
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int x = x0 + j;
+        float acc;
+        if (KS == 3) {
+            // SymmRowSmallVec_32f: fma(centre, k1, (l + r) * k0); a last odd column is OpenCV's scalar tail
+            const float lr = __fadd_rn(v[j], v[j + 2]);
+            acc = x < (W & ~1) ? fmaf(v[j + 1], bt.k[1], __fmul_rn(lr, bt.k[0])) : fmaf(lr, bt.k[0], __fmul_rn(v[j + 1], bt.k[1]));
+        } else {
+            // x0 is a multiple of 4 and W % 4 == 0 here: every output lies in the vectorised part (x < (W & ~3))
+            acc = __fmul_rn(v[j], bt.k[0]);
+#pragma unroll
+            for (int i = 1; i < KS; i++) acc = fmaf(v[j + i], bt.k[i], acc);
+        }
+        o[j] = acc;
+    }
+    *reinterpret_cast<float4*>(out + ((int64_t)b * H + y) * W + x0) = make_float4(o[0], o[1], o[2], o[3]);
+}
+
+template <int R>
+__global__ void __launch_bounds__(128)
+k_blur_cols4(const float* __restrict__ in, float* __restrict__ out, int H, int W, BlurTaps bt)
+{
+    constexpr int KS = 2 * R + 1;
+    const int x = blockIdx.x * 128 + threadIdx.x;
+    const int y0 = blockIdx.y * 4;
+    const int b = blockIdx.z;
+    if (x >= W) return;
+    const float* s = in + (int64_t)b * H * W + x;
+    float v[4 + 2 * R];
+    if (y0 >= R && y0 + 3 + R < H) {
+#pragma unroll
+        for (int i = 0; i < 4 + 2 * R; i++) v[i] = __ldg(s + (int64_t)(y0 - R + i) * W);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4 + 2 * R; i++) v[i] = __ldg(s + (int64_t)reflect101(y0 - R + i, H) * W);
+    }
+    const bool fused = (KS == 3) || x < (W & ~7);  // SymmColumnVec_32f covers multiples of 8 lanes
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        if (y0 + j >= H) break;
+        float acc = __fmul_rn(v[j + R], bt.k[R]);
+#pragma unroll
+        for (int i = 1; i <= R; i++) {
+            const float ac = __fadd_rn(v[j + R + i], v[j + R - i]);
+            acc = fused ? fmaf(ac, bt.k[R + i], acc) : __fadd_rn(acc, __fmul_rn(ac, bt.k[R + i]));
+        }
+        out[((int64_t)b * H + y0 + j) * W + x] = acc;
+    }
+}
+
 int launch_blur_rows(const float* in, int64_t in_ss, int64_t in_rs, SlotMap in_map, float* out, int n, int H,
                      int W, const BlurTaps& bt, cudaStream_t st)
 {
+    const bool win4 = (bt.ksz == 3 || bt.ksz == 7 || bt.ksz == 17) && W % 4 == 0 && W >= 4 + bt.ksz &&
+                      (reinterpret_cast<uintptr_t>(out) & 15) == 0 && H <= 65535;
     for (int b0 = 0; b0 < n; b0 += 65535) {
         int nb = n - b0 < 65535 ? n - b0 : 65535;
         SlotMap m = in_map;
         m.base += b0;
-        dim3 grid((unsigned)cdiv(W, 128), (unsigned)H, (unsigned)nb);
         ProfScope ps(K_BLUR_ROWS, 8.0 * nb * H * W, st);
+        if (win4) {
+            dim3 grid((unsigned)cdiv(W, 512), (unsigned)H, (unsigned)nb);
+            float* o = out + (int64_t)b0 * H * W;
+            if (bt.ksz == 3) k_blur_rows4<1><<<grid, 128, 0, st>>>(in, in_ss, in_rs, m, o, H, W, bt);
+            else if (bt.ksz == 7) k_blur_rows4<3><<<grid, 128, 0, st>>>(in, in_ss, in_rs, m, o, H, W, bt);
+            else k_blur_rows4<8><<<grid, 128, 0, st>>>(in, in_ss, in_rs, m, o, H, W, bt);
+            FDN_LAUNCHED("k_blur_rows4");
+            continue;
+        }
+        dim3 grid((unsigned)cdiv(W, 128), (unsigned)H, (unsigned)nb);
         k_blur_rows<<<grid, 128, 0, st>>>(in, in_ss, in_rs, m, out + (int64_t)b0 * H * W, H, W, bt);
         FDN_LAUNCHED("k_blur_rows");
     }
@@ -193,11 +278,22 @@ int launch_blur_rows(const float* in, int64_t in_ss, int64_t in_rs, SlotMap in_m
 
 int launch_blur_cols(const float* in, float* out, int n, int H, int W, const BlurTaps& bt, cudaStream_t st)
 {
+    const bool win4 = (bt.ksz == 3 || bt.ksz == 7 || bt.ksz == 17) && H >= 4 + bt.ksz;
     for (int b0 = 0; b0 < n; b0 += 65535) {
         int nb = n - b0 < 65535 ? n - b0 : 65535;
-        dim3 grid((unsigned)cdiv(W, 128), (unsigned)H, (unsigned)nb);
         ProfScope ps(K_BLUR_COLS, 8.0 * nb * H * W, st);
-        k_blur_cols<<<grid, 128, 0, st>>>(in + (int64_t)b0 * H * W, out + (int64_t)b0 * H * W, H, W, bt);
+        const float* i_ = in + (int64_t)b0 * H * W;
+        float* o_ = out + (int64_t)b0 * H * W;
+        if (win4) {
+            dim3 grid((unsigned)cdiv(W, 128), (unsigned)cdiv(H, 4), (unsigned)nb);
+            if (bt.ksz == 3) k_blur_cols4<1><<<grid, 128, 0, st>>>(i_, o_, H, W, bt);
+            else if (bt.ksz == 7) k_blur_cols4<3><<<grid, 128, 0, st>>>(i_, o_, H, W, bt);
+            else k_blur_cols4<8><<<grid, 128, 0, st>>>(i_, o_, H, W, bt);
+            FDN_LAUNCHED("k_blur_cols4");
+            continue;
+        }
+        dim3 grid((unsigned)cdiv(W, 128), (unsigned)H, (unsigned)nb);
+        k_blur_cols<<<grid, 128, 0, st>>>(i_, o_, H, W, bt);
         FDN_LAUNCHED("k_blur_cols");
     }
     return FDN_OK;
