@@ -853,15 +853,23 @@ int flow_iter_scratch_init(void* scratch, size_t bytes, cudaStream_t st)
     return FDN_OK;
 }
 
+// function attributes are per device: remember which devices of this process have them
+static bool first_use_on_device(bool (&seen)[64])
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+    if (seen[dev]) return false;
+    seen[dev] = true;
+    return true;
+}
+
 template <int CW, int TR, int MT, int MINB>
 static int launch_flow_variant(const FlowIterArgs& a, dim3 grid, size_t smem, cudaStream_t st)
 {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool seen[64] = {};
+    if (first_use_on_device(seen))
         FDN_CUDA(cudaFuncSetAttribute(k_flow_iter<CW, TR, MT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       200 * 1024));
-        attr_set = true;
-    }
     k_flow_iter<CW, TR, MT, MINB><<<grid, CW + 32, smem, st>>>(a);
     return FDN_OK;
 }
@@ -905,8 +913,8 @@ int launch_flow_iter(const float* R, int64_t R_stride, SlotMap map0, SlotMap map
         FDN_CHECK_ARG(a.strips <= FDN_MAX_STRIPS, "image too wide (%d strips)", a.strips);
         wa.ticket = reinterpret_cast<unsigned*>(static_cast<char*>(scratch) + flow_flag_bytes(n));
         wa.packets = reinterpret_cast<ulonglong2*>(static_cast<char*>(scratch) + flow_flag_bytes(n) + kFlowTicketBytes);
-        static bool attr_set = false;
-        if (!attr_set) {
+        static bool seen[64] = {};
+        if (first_use_on_device(seen)) {
             FDN_CUDA(cudaFuncSetAttribute(k_flow_iter_ws<2, FDN_WS_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)WsCfg2::smem_bytes));
             // leave the rest of the SM's L1/shared array to L1: the R1 rows a strip walks over live there
@@ -919,7 +927,6 @@ int launch_flow_iter(const float* R, int64_t R_stride, SlotMap map0, SlotMap map
                 fprintf(stderr, "[fdn] k_flow_iter_ws: %d blocks/SM, %zu B shared memory per block\n", nb,
                         (size_t)WsCfg2::smem_bytes);
             }
-            attr_set = true;
         }
         if ((unsigned)g_flow_epoch == 0) g_flow_epoch++;   // the packet tag is the low word of the epoch, never 0
         wa.tag = (unsigned)g_flow_epoch;
