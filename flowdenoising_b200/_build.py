@@ -66,5 +66,18 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_locked() -> str:
+    """build() under an exclusive file lock: the ranks of a multi-GPU run that all find the library stale must not
+    write the same objects concurrently (the first one builds, the others wait and find it fresh)."""
+    import fcntl
+    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    with open(os.path.join(HERE, "build", ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return build()
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
 if __name__ == "__main__":
     print(build(force=True, verbose=True))

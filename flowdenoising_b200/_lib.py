@@ -63,6 +63,9 @@ SIGNATURES = {
     "fdn_flow_iteration_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "fdn_flow_iteration": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_void_p, C.c_size_t, C.c_void_p]),
+    "fdn_flow_iterations": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                      C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "fdn_set_flow_iter_variant": (None, [C.c_int]),
     "fdn_flow_area_down": (C.c_int, [c_f32p, C.c_int, C.c_int, C.c_int, c_f32p, C.c_int, C.c_int, C.c_float,
                                      C.c_void_p]),
     "fdn_flow_upsample": (C.c_int, [c_f32p, C.c_int, C.c_int, C.c_int, c_f32p, C.c_int, C.c_int, C.c_void_p]),
@@ -87,17 +90,26 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB
-    if _build.needs_build():
-        try:
-            _build.build()
-        except Exception as e:  # no nvcc, compile error ...
-            if not os.path.exists(path):
-                raise FdnError(f"libfdn_b200.so is missing and could not be built ({e}); there is no CPU "
-                               f"fallback. Run `python -m flowdenoising_b200._build`.") from e
+    path = os.environ.get("FDN_LIB_PATH")   # development: a build variant (tools/build_variant.py)
+    lab = path is not None
+    if not lab:
+        path = _build.LIB
+        if _build.needs_build():
+            try:
+                _build.build_locked()
+            except Exception as e:  # no nvcc, compile error ...
+                if not os.path.exists(path):
+                    raise FdnError(f"libfdn_b200.so is missing and could not be built ({e}); there is no CPU "
+                                   f"fallback. Run `python -m flowdenoising_b200._build`.") from e
+                # a stale library must never be used silently: its ABI or numerics may not match the sources
+                raise FdnError(f"libfdn_b200.so is older than its sources and the rebuild failed ({e})") from e
     lib = C.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
-        fn = getattr(lib, name)  # AttributeError = ABI mismatch, fail loudly
+        fn = getattr(lib, name, None)
+        if fn is None:
+            if lab:
+                continue   # an older build variant under comparison
+            raise AttributeError(f"{name} is declared in include/fdn_b200.h but not exported by {path}")
         fn.restype = res
         fn.argtypes = args
     _lib = lib

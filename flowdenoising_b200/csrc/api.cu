@@ -97,7 +97,7 @@ static int make_geometry(int H, int W, int levels, Geometry* g)
 
 static int check_of(const fdn_of_params* of)
 {
-    FDN_CHECK_ARG(of->winsize >= 1 && of->winsize <= 33, "winsize %d unsupported (1..33)", of->winsize);
+    FDN_CHECK_ARG(of->winsize >= 1 && of->winsize <= 31, "winsize %d unsupported (1..31)", of->winsize);
     FDN_CHECK_ARG(of->iterations >= 1, "iterations must be >= 1");
     FDN_CHECK_ARG(of->poly_n >= 1 && of->poly_n <= 7, "poly_n %d unsupported (1..7)", of->poly_n);
     FDN_CHECK_ARG(of->levels >= 0, "levels must be >= 0");
@@ -134,16 +134,26 @@ static int build_R(const float* in, int64_t in_ss, int64_t in_rs, SlotMap in_map
 
 // Farneback for a batch of n pairs whose polynomial expansions are cached in R (pair b: prev = map0.slot(b),
 // next = map1.slot(b)). P: (n, H, W, 2) initial flow in / final flow out. S1, S2: scratch of the same size.
+// The iterations of a level rotate through the three buffers (launch_flow_level); the level transfers are placed
+// so that, for the usual iteration counts, the last iteration of level 0 writes P itself.
 static int farneback_batch(const float* R, const Geometry& g, SlotMap map0, SlotMap map1, float* P, float* S1,
-                           float* S2, int n, int H, int W, const fdn_of_params& of, void* scratch, size_t scratch_bytes,
+                           float* S2, int n, int H, int W, const fdn_of_params& of, const FlowScratch& fs,
                            cudaStream_t st)
 {
     int rc;
     float* cur = nullptr;
     int ch = 0, cw = 0;
+    const int iters = of.iterations;
     for (int k = g.nl; k >= 0; k--) {
         const int h = g.hs[k], w = g.ws[k];
         const size_t fbytes = sizeof(float) * 2 * (size_t)n * h * w;
+        // where this level's input flow should live so that its result ends up where the next step wants it:
+        // the result of `iters` iterations lands in rotation slot iters % 3 of {cur, a, b}
+        //   level 0: result in P      -> iters % 3 == 0: cur = P;  else cur != P and P in slot iters % 3
+        //   level k > 0: result != P  -> (the next upsample can then write P if it has to)
+        float* want_cur;
+        if (k == 0) want_cur = (iters % 3 == 0) ? P : nullptr;   // nullptr: anything but P
+        else want_cur = nullptr;
         if (k == g.nl) {
             if (of.use_prev_flow) {
                 if (k == 0) {
@@ -157,19 +167,27 @@ static int farneback_batch(const float* R, const Geometry& g, SlotMap map0, Slot
                 FDN_CUDA(cudaMemsetAsync(cur, 0, fbytes, st));
             }
         } else {
-            float* other = (cur == S1) ? S2 : S1;
-            if ((rc = launch_flow_upsample(cur, n, ch, cw, other, h, w, st))) return rc;
-            cur = other;
-        }
-        for (int it = 0; it < of.iterations; it++) {
-            const bool last = (k == 0 && it == of.iterations - 1);
-            float* dst = last ? P : ((cur == S1) ? S2 : S1);
-            if (dst == cur) dst = S1;  // single level, single iteration: P -> S1, copied back below
-            if ((rc = launch_flow_iter(R + g.R_off[k], (int64_t)g.R_slot, map0, map1, cur, dst, n, h, w, of.winsize,
-                                       scratch, scratch_bytes, st)))
-                return rc;
+            float* dst = want_cur ? want_cur : (cur == S1 ? S2 : S1);   // cur != P here (see below)
+            if ((rc = launch_flow_upsample(cur, n, ch, cw, dst, h, w, st))) return rc;
             cur = dst;
         }
+        // order the other two buffers: the rotation slot of the result (iters % 3: 0 -> cur, 1 -> a, 2 -> b) must be P at
+        // level 0 and should not be P above it (so that the next upsample may write P)
+        float* others[2];
+        int no = 0;
+        float* const all3[3] = {P, S1, S2};
+        for (int q = 0; q < 3; q++)
+            if (all3[q] != cur) others[no++] = all3[q];
+        float* a = others[0];
+        float* b = others[1];
+        const int slot = iters % 3;
+        const bool want_P = (k == 0);
+        if ((slot == 1 && (a == P) != want_P) || (slot == 2 && (b == P) != want_P)) { float* t = a; a = b; b = t; }
+        float* res = nullptr;
+        if ((rc = launch_flow_level(R + g.R_off[k], (int64_t)g.R_slot, map0, map1, cur, a, b, n, h, w, of.winsize, iters,
+                                    fs, st, &res)))
+            return rc;
+        cur = res;
         ch = h; cw = w;
     }
     if (cur != P) FDN_CUDA(cudaMemcpyAsync(P, cur, sizeof(float) * 2 * (size_t)n * H * W, cudaMemcpyDeviceToDevice, st));
@@ -179,7 +197,7 @@ static int farneback_batch(const float* R, const Geometry& g, SlotMap map0, Slot
 struct PassPlan {
     int chunk, r, slots, full_wrap;
     Geometry g;
-    size_t off_R, off_P, off_S1, off_S2, off_scratch, scratch_bytes, total;
+    size_t off_R, off_P, off_S1, off_S2, off_stash, off_scratch, scratch_bytes, total;
 };
 
 static int make_plan(const fdn_view& v, int klen, const fdn_of_params& of, int chunk, PassPlan* p)
@@ -201,13 +219,16 @@ static int make_plan(const fdn_view& v, int klen, const fdn_of_params& of, int c
     p->chunk = chunk;
     p->full_wrap = v.periodic && (chunk + 2 * p->r >= v.n_in);
     p->slots = p->full_wrap ? v.n_in : chunk + 2 * p->r;
-    const size_t fl = sizeof(float) * 2 * (size_t)chunk * v.H * v.W;
+    // both chain directions advance together: 2 * chunk image pairs per launch
+    const size_t px = (size_t)chunk * v.H * v.W;
+    const size_t fl = sizeof(float) * 2 * 2 * px;
     size_t off = 0;
     p->off_R = off;  off += align_up(sizeof(float) * p->g.R_slot * (size_t)p->slots, 256);
     p->off_P = off;  off += align_up(fl, 256);
     p->off_S1 = off; off += align_up(fl, 256);
     p->off_S2 = off; off += align_up(fl, 256);
-    p->scratch_bytes = flow_iter_scratch_bytes(chunk, v.H, v.W);  // level 0 is the largest
+    p->off_stash = off; off += align_up(sizeof(float) * px * (size_t)p->r, 256);   // remapped forward neighbours
+    p->scratch_bytes = flow_iter_scratch_bytes(2 * chunk, v.H, v.W);  // level 0 is the largest
     p->off_scratch = off; off += align_up(p->scratch_bytes, 256);
     p->total = off;
     return FDN_OK;
@@ -229,8 +250,10 @@ static int filter_axis_of(const float* d_in, float* d_out, const fdn_view& v, co
     float* P = reinterpret_cast<float*>(base + p.off_P);
     float* S1 = reinterpret_cast<float*>(base + p.off_S1);
     float* S2 = reinterpret_cast<float*>(base + p.off_S2);
-    void* scratch = base + p.off_scratch;
-    if ((rc = flow_iter_scratch_init(scratch, p.scratch_bytes, st))) return rc;
+    float* stash = reinterpret_cast<float*>(base + p.off_stash);
+    FlowScratch fs;
+    if ((rc = flow_scratch_make(base + p.off_scratch, p.scratch_bytes, 2 * p.chunk, H, W, &fs))) return rc;
+    if ((rc = flow_iter_scratch_init(fs, st))) return rc;
     PolyConsts pc;
     prepare_poly_consts(of.poly_n, of.poly_sigma, &pc);
     const int wrap_in = v.periodic ? v.n_in : 0;
@@ -255,33 +278,29 @@ static int filter_axis_of(const float* d_in, float* d_out, const fdn_view& v, co
             }
             cache_full = p.full_wrap;
         }
-        // ---- chains ----
-        SlotMap map0 = p.full_wrap ? SlotMap{c0 + v.halo, v.n_in} : SlotMap{r, 0};
+        // ---- the two chains (src/flowdenoising.py:311-316 backward, :319-324 forward) advance together: image
+        //      pairs [0, C) = (slice, slice - d), pairs [C, 2C) = (slice, slice + d) ----
+        const int cbase = p.full_wrap ? c0 + v.halo : r;             // R slot of the chunk's first centre slice
+        const int swrap = p.full_wrap ? v.n_in : 0;
+        SlotMap map0{cbase, swrap, C, cbase};
         float* acc = d_out + (int64_t)c0 * v.out_slice_stride;
-        bool first = true;
-        const size_t fbytes = sizeof(float) * 2 * (size_t)C * H * W;
-        for (int dir = 0; dir < 2; dir++) {
-            if (dir == 1) {  // centre tap between the two chains (src/flowdenoising.py:317)
-                SlotMap cmap{c0 + v.halo, wrap_in};
-                if ((rc = launch_warp_acc(d_in, v.in_slice_stride, v.in_row_stride, cmap, nullptr, kernel[r], acc,
-                                          v.out_slice_stride, v.out_row_stride, C, H, W, first ? 1 : 0, st)))
-                    return rc;
-                first = false;
-            }
-            if (r > 0) FDN_CUDA(cudaMemsetAsync(P, 0, fbytes, st));  // prev_flow = zeros (:310, :318)
-            for (int d = 1; d <= r; d++) {
-                const int off = dir == 0 ? -d : d;
-                const int tap = r + off;  // kernel index i (backward: r-1..0, forward: r+1..2r)
-                SlotMap map1 = p.full_wrap ? SlotMap{c0 + v.halo + off, v.n_in} : SlotMap{r + off, 0};
-                if ((rc = farneback_batch(R, p.g, map0, map1, P, S1, S2, C, H, W, of, scratch, p.scratch_bytes, st)))
-                    return rc;
-                SlotMap nmap{c0 + v.halo + off, wrap_in};
-                if ((rc = launch_warp_acc(d_in, v.in_slice_stride, v.in_row_stride, nmap, P, kernel[tap], acc,
-                                          v.out_slice_stride, v.out_row_stride, C, H, W, first ? 1 : 0, st)))
-                    return rc;
-                first = false;
-            }
+        const size_t fbytes = sizeof(float) * 2 * 2 * (size_t)C * H * W;
+        if (r > 0) FDN_CUDA(cudaMemsetAsync(P, 0, fbytes, st));  // prev_flow = zeros (:310, :318)
+        for (int d = 1; d <= r; d++) {
+            SlotMap map1{cbase - d, swrap, C, cbase + d};
+            if ((rc = farneback_batch(R, p.g, map0, map1, P, S1, S2, 2 * C, H, W, of, fs, st))) return rc;
+            // backward neighbour: tap r-d accumulated now (reference order -1, -2, ..., -r); forward neighbour:
+            // remapped now, applied by launch_acc_finish after the centre tap (order 0, +1, ..., +r)
+            SlotMap nmap{c0 + v.halo - d, wrap_in, C, c0 + v.halo + d};
+            if ((rc = launch_warp_pair(d_in, v.in_slice_stride, v.in_row_stride, nmap, P, kernel[r - d], acc,
+                                       v.out_slice_stride, v.out_row_stride, stash + (size_t)(d - 1) * C * H * W, C, H, W,
+                                       d == 1 ? 1 : 0, st)))
+                return rc;
         }
+        SlotMap cmap{c0 + v.halo, wrap_in};
+        if ((rc = launch_acc_finish(d_in, v.in_slice_stride, v.in_row_stride, cmap, stash, r, kernel + r, acc,
+                                    v.out_slice_stride, v.out_row_stride, C, H, W, r > 0 ? 1 : 0, st)))
+            return rc;
     }
     return FDN_OK;
 }
@@ -457,18 +476,40 @@ size_t fdn_polyexp_floats(int h, int w) { return R_image_floats(h, w); }
 
 size_t fdn_flow_iteration_scratch_bytes(int n, int h, int w) { return flow_iter_scratch_bytes(n, h, w); }
 
+void fdn_set_flow_iter_variant(int variant) { set_flow_iter_variant(variant); }
+
+int fdn_flow_iterations(const float* d_R0, const float* d_R1, float* d_flow, float* d_tmp1, float* d_tmp2, int n, int h,
+                        int w, int winsize, int iterations, void* d_scratch, size_t scratch_bytes, void* stream,
+                        float** d_result)
+{
+    FDN_CHECK_ARG(d_R0 && d_R1 && d_flow && d_tmp1 && d_tmp2 && n >= 1 && iterations >= 1 && d_result, "bad argument");
+    // R0 and R1 are separate dense batches: address both relative to R0 with a slot stride of one image
+    const int64_t stride = (int64_t)R_image_floats(h, w);
+    int rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    FlowScratch fs;
+    if ((rc = flow_scratch_make(d_scratch, scratch_bytes, n, h, w, &fs))) return rc;
+    if ((rc = flow_iter_scratch_init(fs, st))) return rc;
+    const ptrdiff_t delta = d_R1 - d_R0;
+    FDN_CHECK_ARG(delta % stride == 0, "R1 - R0 must be a multiple of one image (fdn_polyexp_floats(h, w))");
+    return launch_flow_level(d_R0, stride, SlotMap{0, 0}, SlotMap{(int)(delta / stride), 0}, d_flow, d_tmp1, d_tmp2, n, h,
+                             w, winsize, iterations, fs, st, d_result);
+}
+
 int fdn_flow_iteration(const float* d_R0, const float* d_R1, const float* d_flow_in, float* d_flow_out, int n, int h,
                        int w, int winsize, void* d_scratch, size_t scratch_bytes, void* stream)
 {
     FDN_CHECK_ARG(d_R0 && d_R1 && d_flow_in && d_flow_out && n >= 1, "bad argument");
-    // R0 and R1 are separate dense batches: address both relative to R0 with a slot stride of one image
-    const int64_t stride = (int64_t)R_image_floats(h, w);
-    int rc;
-    if ((rc = flow_iter_scratch_init(d_scratch, scratch_bytes, static_cast<cudaStream_t>(stream)))) return rc;
-    const ptrdiff_t delta = d_R1 - d_R0;
-    FDN_CHECK_ARG(delta % stride == 0, "R1 - R0 must be a multiple of one image (fdn_polyexp_floats(h, w))");
-    return launch_flow_iter(d_R0, stride, SlotMap{0, 0}, SlotMap{(int)(delta / stride), 0}, d_flow_in, d_flow_out, n,
-                            h, w, winsize, d_scratch, scratch_bytes, static_cast<cudaStream_t>(stream));
+    FDN_CHECK_ARG(d_flow_in != d_flow_out, "flow_in and flow_out must not alias");
+    // a single iteration touches two of the three rotation buffers: the third is never dereferenced
+    float* res = nullptr;
+    float* in = const_cast<float*>(d_flow_in);
+    float* dummy = reinterpret_cast<float*>(static_cast<char*>(d_scratch));   // distinct address, unused with 1 iteration
+    int rc = fdn_flow_iterations(d_R0, d_R1, in, d_flow_out, dummy, n, h, w, winsize, 1, d_scratch, scratch_bytes, stream,
+                                 &res);
+    if (rc) return rc;
+    if (res != d_flow_out) { set_error("internal: unexpected result buffer"); return FDN_ERR_INVALID; }
+    return FDN_OK;
 }
 
 int fdn_flow_area_down(const float* d_flow, int n, int H, int W, float* d_out, int h, int w, float scale, void* stream)
@@ -511,9 +552,9 @@ int fdn_farneback(const float* d_prev, const float* d_next, float* d_flow, int n
     float* R = reinterpret_cast<float*>(base);
     float* S1 = reinterpret_cast<float*>(base + align_up(sizeof(float) * g.R_slot * 2 * (size_t)n, 256));
     float* S2 = reinterpret_cast<float*>(reinterpret_cast<char*>(S1) + fl);
-    void* scratch = reinterpret_cast<char*>(S2) + fl;
-    const size_t scratch_bytes = flow_iter_scratch_bytes(n, H, W);
-    if ((rc = flow_iter_scratch_init(scratch, scratch_bytes, st))) return rc;
+    FlowScratch fs;
+    if ((rc = flow_scratch_make(reinterpret_cast<char*>(S2) + fl, flow_iter_scratch_bytes(n, H, W), n, H, W, &fs))) return rc;
+    if ((rc = flow_iter_scratch_init(fs, st))) return rc;
     PolyConsts pc;
     prepare_poly_consts(of->poly_n, of->poly_sigma, &pc);
     // slots [0, n): prev images, [n, 2n): next images. S1/S2 double as image scratch (3*n*H*W floats needed).
@@ -524,7 +565,7 @@ int fdn_farneback(const float* d_prev, const float* d_next, float* d_flow, int n
         return rc;
     if ((rc = build_R(d_next, (int64_t)H * W, W, SlotMap{0, 0}, n, H, W, g, pc, R, SlotMap{n, 0}, tmpA, tmpB, img, st)))
         return rc;
-    return farneback_batch(R, g, SlotMap{0, 0}, SlotMap{n, 0}, d_flow, S1, S2, n, H, W, *of, scratch, scratch_bytes, st);
+    return farneback_batch(R, g, SlotMap{0, 0}, SlotMap{n, 0}, d_flow, S1, S2, n, H, W, *of, fs, st);
 }
 
 int fdn_warp_accumulate(const float* d_neigh, int64_t neigh_slice_stride, int64_t neigh_row_stride,

@@ -24,6 +24,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "fdn_internal.cuh"
 
 namespace fdn {
@@ -35,12 +37,14 @@ struct FlowIterArgs {
     const float* flow_in;
     float* flow_out;
     int h, w, m;
+    int n;              // image pairs (grid = n * strips blocks)
     int LS;             // shared tile line stride in doubles (== 1 mod 16)
     int strips;
     double scale;       // 1 / winsize^2
     double* carry;      // [n][strips][h][5]
     unsigned long long* flags;  // [n][strips]
     unsigned long long epoch;
+    unsigned* ctl;      // [0] tickets taken, [1] blocks finished (both 0 between launches)
 };
 
 // ROWCHK = false: the caller guarantees 5 <= y < h - 5, so the border weight reduces to the column factor `sx`
@@ -135,8 +139,13 @@ k_flow_iter(FlowIterArgs a)
     float* ring = reinterpret_cast<float*>(smem_raw + sizeof(double) * TR * 5 * LS);  // [RR][5][NT]
 
     const int t = threadIdx.x;
-    const int k = blockIdx.x;  // strip
-    const int b = blockIdx.y;  // image pair
+    // (pair, strip) from a ticket, strip fastest: a strip spin-waits on the strip to its left, which therefore must
+    // already be running whatever order the hardware dispatches blocks in
+    __shared__ int s_ticket;
+    if (t == 0) s_ticket = (int)atomicAdd(a.ctl, 1u);
+    __syncthreads();
+    const int k = s_ticket % a.strips;  // strip
+    const int b = s_ticket / a.strips;  // image pair
     const int x0 = k * CW;
     // tile position q <-> column x0 - m - 1 + q, q in [0, CW + 2m + 1)
     int q;
@@ -352,6 +361,10 @@ k_flow_iter(FlowIterArgs a)
         }
         __syncthreads();
     }
+    if (t == 0) {   // the last block to finish re-arms the ticket counters for the next launch
+        __threadfence();
+        if (atomicAdd(a.ctl + 1, 1u) == gridDim.x - 1) { a.ctl[0] = 0; a.ctl[1] = 0; }
+    }
 }
 
 
@@ -362,19 +375,29 @@ k_flow_iter(FlowIterArgs a)
 //     warpgroup one "scan" warp runs phase H and three "solve" warps run phase S. The column sums of a tile go into
 //     one of TWO shared-memory tiles, so the scan / solve of tile j overlap phase V of tiles j+1 and j+2. Registers
 //     are moved between the warpgroups with setmaxnreg (176 per column thread, 80 per scan / solve thread, 2 blocks
-//     per SM); hand-offs are named barriers (bar.arrive / bar.sync) and two progress counters in shared memory;
+//     per SM); hand-offs are hardware barriers only -- named barriers (bar.arrive / bar.sync) between the column
+//     warps and the scan / solve warps, and one mbarrier per 32-column chunk of a tile on which the solve warps
+//     sleep until the scan has passed (round 1 polled a shared-memory counter here: a fifth of all issued
+//     instructions and of the L1 / shared-memory pipe's wavefronts were that poll);
 //   * the ring of the last 2m+2 rows of M lives in REGISTERS: a tile is one ring period (TR = 2m+2 rows), so every
 //     ring slot is a compile-time constant of the unrolled row loop;
 //   * phase V is branch-free (selects, clamped gather addresses): the m+1 rows of half a tile form one straight-line
 //     block whose dependency chains the compiler interleaves. The bilinear gather reads R1 through L1 -- the
 //     kernel's shared memory is small (62 KB per block), so about 100 KB of L1 remain per SM; every gather also
 //     prefetches (prefetch.global.L1) the R1 line the same column will need FDN_WS_PF rows further down, and the
-//     R0 / flow rows, read once, bypass L1 (ld.global.nc.L1::no_allocate) and are register-prefetched a tile ahead;
+//     R0 / flow rows, read once, bypass L1 and are register-prefetched a tile ahead;
 //   * carries between strips travel as self-validating packets {32 data bits, 32-bit launch tag} (two per double,
 //     one 16-byte store): no fences, no flag, only the 5*TR scanning lanes ever wait for the left strip;
 //   * phase H reads a line once, 128 bits at a time, through a sliding register window, forms the differences of
 //     the next 8 columns while the dependent DADD chain of the current 8 runs, and stores 128 bits at a time;
-//   * phase S follows the scan through the tile in chunks of 32 columns (a full tile is one straight-line block).
+//   * phase S follows the scan through the tile in chunks of 32 columns (a full tile is one straight-line block);
+//   * ONE launch runs up to three consecutive Farneback iterations of a level: a block's work item
+//     (iteration, pair, strip) comes from a ticket counter (iteration slowest, strip fastest). A strip waits for the
+//     strip to its left, and an iteration of a pair for all strips of its previous iteration (a counter per
+//     (iteration, pair)); both are always held by blocks with EARLIER tickets, which are resident or finished --
+//     forward progress does not depend on the order the hardware dispatches blocks in. Three iterations rotate
+//     through three flow buffers, so no buffer is read after it was written in the same launch by another SM
+//     except through L2 (flow loads are ld.global.cg). The last warp to leave re-arms all counters.
 // Same arithmetic, same order of operations, same bits as k_flow_iter. Needs w % 4 == 0.
 // ------------------------------------------------------------------------------------------------
 struct RowIn {
@@ -390,9 +413,10 @@ struct WsCfg {
     static constexpr int SR = MT + 1;       // rows per straight-line block
     static constexpr int HALO = 2 * MT + 1;
     static constexpr int CWMAX = (NT - HALO) & ~3;
+    static constexpr int NCH = (CWMAX + 31) / 32;   // 32-column chunks of a strip (scan -> solve hand-off)
     static constexpr int LS = NT + 2;       // tile line stride in doubles (even: every line is 16-byte aligned)
     static constexpr size_t tiles_bytes = 2 * sizeof(double) * TR * 5 * LS + 128;   // two tiles (+ the scan's read-ahead past the last line)
-    static constexpr size_t smem_bytes = tiles_bytes + 16;                    // + the scan's progress counters, the ticket
+    static constexpr size_t smem_bytes = tiles_bytes + 8 * 2 * NCH + 16;      // + the chunk mbarriers, the ticket
     static_assert(5 * TR <= 32, "phase H runs in one warp");
 };
 
@@ -477,23 +501,31 @@ __device__ __forceinline__ void ws_matrices_px(const RowIn& in, const Taps& tp, 
 #else
 #define FDN_WS_EXP(bit) (0)
 #endif
-#ifndef FDN_WS_POLL_NS
-#define FDN_WS_POLL_NS 200   // the solve warps have slack: poll the scan's progress coarsely, leave the issue slots to phase V
-#endif
 #ifndef FDN_WS_HC
 #define FDN_WS_HC 8
 #endif
 #ifndef FDN_WS_PF
 #define FDN_WS_PF 6
 #endif
+#ifndef FDN_WS_L2PF
+#define FDN_WS_L2PF 0
+#endif
+#define FDN_WS_MAX_ITERS 3   // iterations per launch: one flow buffer per iteration, none read after being rewritten
 
 struct WsArgs {
-    FlowIterArgs a;
-    int CW;
-    int exp;               // 0 in product builds; phase-removal timing experiments with -DFDN_WS_EXPERIMENTS (FDN_EXP)
-    unsigned tag;          // launch tag of the carry packets (never 0)
-    ulonglong2* packets;   // [n][strips][h][5]: {lo32 | tag << 32, hi32 | tag << 32}
-    unsigned* ticket;      // [2]: tickets taken, blocks that have taken one (both 0 between launches)
+    const float* R;         // level base inside slot 0
+    int64_t R_stride;       // floats per slot
+    SlotMap map0, map1;
+    const float* fin[FDN_WS_MAX_ITERS];    // flow read / written by iteration i of this launch
+    float* fout[FDN_WS_MAX_ITERS];
+    int n, iters;           // image pairs, iterations in this launch
+    int h, w, CW, strips;
+    double scale;           // 1 / winsize^2
+    int exp;                // 0 in product builds; phase-removal timing experiments with -DFDN_WS_EXPERIMENTS (FDN_EXP)
+    unsigned tag;           // iteration i tags its carry packets with tag + i (never 0)
+    ulonglong2* packets;    // [n][strips][h][5]: {lo32 | tag << 32, hi32 | tag << 32}
+    unsigned* ctl;          // [0] tickets taken, [1] warps that have finished (both 0 between launches)
+    unsigned* done;         // [iters][n]: strips of (iteration, pair) that have written all their flow (0 between launches)
 };
 
 // named barriers (id 0 is __syncthreads)
@@ -505,10 +537,17 @@ __device__ __forceinline__ void nbar_arrive(int id, int count)
 {
     asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(count) : "memory");
 }
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 
 // Roles and hand-offs:
-//   column warps:  V(j) -> arrive FULL[j&1] -> wait DONE[(j-1)&1] -> S(j-1) -> barrier among column warps -> V(j+1) ...
-//   scan warp:     wait FULL[j&1] -> H(j) in place -> arrive DONE[j&1] -> ...
+//   column warps:  [wait FREE[j&1]] -> V(j) -> arrive FULL[j&1] -> V(j+1) ...
+//   scan warp:     wait FULL[j&1] -> H(j) in place, arriving on CHUNK[j&1][q] every 32 columns
+//   solve warps:   wait CHUNK[j&1][q] -> S(j) for chunk q -> ... -> arrive FREE[j&1]
 // Registers: the kernel is compiled for (65536 / 2 blocks / 256 threads) = 128 per thread; the column warpgroup then
 // takes 176 (setmaxnreg.inc) and the scan warpgroup keeps 80 (setmaxnreg.dec).
 template <int MT, int NT_>
@@ -516,39 +555,55 @@ __global__ void __launch_bounds__(NT_ + 128, 2)
 k_flow_iter_ws(WsArgs wa)
 {
     using C = WsCfg<MT, NT_>;
-    constexpr int NT = C::NT, TR = C::TR, SR = C::SR, RR = C::TR, LS = C::LS, m = MT;
-    constexpr int BAR_FULL = 1, BAR_FREE = 5;
-    const FlowIterArgs& a = wa.a;
+    constexpr int NT = C::NT, TR = C::TR, SR = C::SR, RR = C::TR, LS = C::LS, NCH = C::NCH, m = MT;
+    constexpr int BAR_FULL = 1, BAR_FREE = 5, BAR_SOLVED = 7;
+    constexpr unsigned WARPS = (NT + 128) / 32;
     extern __shared__ __align__(128) unsigned char smem_ws[];
     double* tiles = reinterpret_cast<double*>(smem_ws);                       // [2][TR*5][LS]
-    volatile int* prog = reinterpret_cast<volatile int*>(smem_ws + C::tiles_bytes);   // [2]: j * 4096 + columns scanned
-    const int h = a.h, w = a.w;
+    unsigned long long* chunk_bar = reinterpret_cast<unsigned long long*>(smem_ws + C::tiles_bytes);   // [2][NCH]
+    volatile int* sh = reinterpret_cast<volatile int*>(smem_ws + C::tiles_bytes + 8 * 2 * NCH);
+    const int h = wa.h, w = wa.w;
     const int t = threadIdx.x;
-    // Which (pair, strip) this block works on is decided by a ticket, not by blockIdx: a strip waits for the strip to
-    // its left, so the left strip must already be running. Tickets are handed out in the order blocks actually start
-    // (strip index fastest), whatever order the hardware dispatches them in. The block that takes the last ticket
-    // re-arms both counters for the next launch on the stream.
+    const unsigned per_it = (unsigned)wa.n * (unsigned)wa.strips;
     if (t == 0) {
-        const unsigned total = gridDim.x * gridDim.y;
-        const unsigned tk = atomicAdd(wa.ticket, 1u);
-        prog[2] = (int)tk;
-        if (atomicAdd(wa.ticket + 1, 1u) == total - 1) {   // every ticket has been taken
-            wa.ticket[0] = 0;
-            wa.ticket[1] = 0;
+        const unsigned tk = atomicAdd(wa.ctl, 1u);
+        sh[0] = (int)tk;
+        const unsigned it0 = tk / per_it;
+        if (it0 > 0) {   // every strip of this pair's previous iteration must have written its flow
+            const unsigned b0 = (tk - it0 * per_it) / (unsigned)wa.strips;
+            const unsigned* dn = wa.done + (size_t)(it0 - 1) * wa.n + b0;
+            while (ld_acquire_u32(dn) < (unsigned)wa.strips) __nanosleep(200);
         }
     }
-    if (t < 2) prog[t] = -1;
+    if (t < 2 * NCH) mbar_init(smem_u32(chunk_bar + t), 1);
     __syncthreads();
-    const int ticket = prog[2];
-    const int k = ticket % (int)gridDim.x;  // strip
-    const int b = ticket / (int)gridDim.x;  // image pair
+    const unsigned ticket = (unsigned)sh[0];
+    const int it = (int)(ticket / per_it);
+    const unsigned rem = ticket - (unsigned)it * per_it;
+    const int b = (int)(rem / (unsigned)wa.strips);   // image pair
+    const int k = (int)(rem - (unsigned)b * wa.strips);   // strip
+    const unsigned tag = wa.tag + (unsigned)it;
     const int CW = wa.CW;
     const int x0 = k * CW;
     const int ncols = min(CW, w - x0);   // multiple of 4
     const int ntiles = (h + TR - 1) / TR;
 
+    // every warp reports when it leaves; the last one of the grid re-arms the counters for the next launch
+    auto warp_exit = [&]() {
+        __syncwarp();
+        unsigned last = 0;
+        if ((t & 31) == 0) {
+            __threadfence();
+            last = atomicAdd(wa.ctl + 1, 1u) == gridDim.x * WARPS - 1u;
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last) {
+            for (int i = t & 31; i < wa.iters * wa.n; i += 32) wa.done[i] = 0;
+            if ((t & 31) == 0) { wa.ctl[0] = 0; wa.ctl[1] = 0; }
+        }
+    };
+
     if (t >= NT) {
-        // =============================== scan warp: phase H ===============================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
         if (t >= NT + 32) {
             // =============================== solve warps: phase S ===============================
@@ -556,11 +611,11 @@ k_flow_iter_ws(WsArgs wa)
             // rows are independent: the compiler interleaves their dependency chains).
             constexpr int NS = 96;   // solving lanes
             const int sl = t - (NT + 32);
-            float2* fout = reinterpret_cast<float2*>(a.flow_out) + (int64_t)b * h * w;
+            float2* fout = reinterpret_cast<float2*>(wa.fout[it]) + (int64_t)b * h * w;
             auto solve_px = [&](const double* tt, int r, float2* dst) {
                 double g[5];
 #pragma unroll
-                for (int c = 0; c < 5; c++) g[c] = __dmul_rn(tt[(r * 5 + c) * LS], a.scale);
+                for (int c = 0; c < 5; c++) g[c] = __dmul_rn(tt[(r * 5 + c) * LS], wa.scale);
                 const double det = __dadd_rn(__dsub_rn(__dmul_rn(g[0], g[2]), __dmul_rn(g[1], g[1])), 1e-3);
                 const double idet = __drcp_rn(det);  // == 1./det correctly rounded, like the IEEE division
                 float2 o;
@@ -569,14 +624,15 @@ k_flow_iter_ws(WsArgs wa)
                 *dst = o;
             };
             const int sw = sl >> 5, sln = sl & 31;
+            const int qlast = (ncols - 1) >> 5;
             for (int j = 0; j < ntiles; j++) {
                 const int y0 = j * TR;
+                const uint32_t bars = smem_u32(chunk_bar + (j & 1) * NCH);
+                const uint32_t parity = (uint32_t)((j >> 1) & 1);
                 // the solve follows the scan through the tile: 32-column chunk q goes to solve warp q % 3 as soon as the
-                // scan warp has published that many columns
-                for (int q = sw; q * 32 < ncols; q += NS / 32) {
-                    const int need = j * 4096 + min(q * 32 + 32, ncols);
-                    while (prog[j & 1] < need) __nanosleep(FDN_WS_POLL_NS);
-                    __threadfence_block();
+                // scan warp has passed it
+                for (int q = sw; q <= qlast; q += NS / 32) {
+                    mbar_wait(bars + 8 * q, parity);
                     const int col = q * 32 + sln;
                     if (col < ncols && !FDN_WS_EXP(8)) {
                         const double* tt = tiles + (j & 1) * TR * 5 * LS + col;
@@ -589,20 +645,31 @@ k_flow_iter_ws(WsArgs wa)
                         }
                     }
                 }
-                // a solve warp without a chunk in this strip (narrow strips) must not run ahead of the tile either
-                while (prog[j & 1] < j * 4096 + ncols) __nanosleep(FDN_WS_POLL_NS);
-                nbar_arrive(BAR_FREE + (j & 1), NS + NT);     // the tile may be overwritten by phase V of tile j+2
+                // a warp without a chunk in this strip (narrow strips) must not run ahead of the tile either: its
+                // arrival below has to count for THIS tile's phase of the FREE barrier
+                mbar_wait(bars + 8 * qlast, parity);
+                nbar_arrive(BAR_FREE + (j & 1), NS + NT);     // this warp is done with the tile (phase V of tile j+2 may overwrite it)
             }
+            if (it + 1 < wa.iters) {   // publish: this strip's flow of iteration `it` is in memory
+                nbar_sync(BAR_SOLVED, NS);
+                if (sl == 0) {
+                    __threadfence();
+                    atomicAdd(wa.done + (size_t)it * wa.n + b, 1u);
+                }
+            }
+            warp_exit();
             return;
         }
+        // =============================== scan warp: phase H ===============================
         const int lane = t - NT;
         const int r = lane / 5, c = lane - r * 5;
-        ulonglong2* pk_out = wa.packets + ((int64_t)b * a.strips + k) * h * 5;
-        const ulonglong2* pk_in = wa.packets + ((int64_t)b * a.strips + max(k - 1, 0)) * h * 5;
+        ulonglong2* pk_out = wa.packets + ((int64_t)b * wa.strips + k) * h * 5;
+        const ulonglong2* pk_in = wa.packets + ((int64_t)b * wa.strips + max(k - 1, 0)) * h * 5;
         constexpr int off = 2 * m + 1;
-        constexpr int HC = FDN_WS_HC;   // columns per chunk of the scan
+        static_assert(off == 5 && FDN_WS_HC == 8, "the sliding window below is written for m = 2, 8-column chunks");
         for (int j = 0; j < ntiles; j++) {
             const int y = j * TR + r;
+            const uint32_t bars = smem_u32(chunk_bar + (j & 1) * NCH);
             nbar_sync(BAR_FULL + (j & 1), NT + 32);
             const unsigned hmask = __ballot_sync(0xffffffffu, lane < 5 * TR && y < h);   // the scanning lanes
             if (lane < 5 * TR && y < h) {
@@ -631,6 +698,12 @@ k_flow_iter_ws(WsArgs wa)
         S = __dadd_rn(S, D[6]); s3.x = S; S = __dadd_rn(S, D[7]); s3.y = S;        \
         l2[4 * (kk)] = s0; l2[4 * (kk) + 1] = s1; l2[4 * (kk) + 2] = s2; l2[4 * (kk) + 3] = s3; \
     }
+                // every 32 columns: wake the solve warp that owns the chunk (the last chunk is announced after the loop)
+#define FDN_CHUNK_DONE(kk)                                                         \
+    if (((kk) & 3) == 0 && 8 * (kk) < ncols) {                                     \
+        __syncwarp(hmask);                                                         \
+        if (lane == 0) mbar_arrive(bars + 8 * (((kk) >> 2) - 1));                  \
+    }
                 const int n8 = ncols >> 3;   // full chunks; ncols % 8 is 0 or 4
                 double2 wa_[4], wb_[4];
                 double d[8];
@@ -646,7 +719,7 @@ k_flow_iter_ws(WsArgs wa)
                 } else {
                     const ulonglong2* src = pk_in + (int64_t)y * 5 + c;
                     ulonglong2 v = __ldcv(src);
-                    while ((unsigned)(v.x >> 32) != wa.tag || (unsigned)(v.y >> 32) != wa.tag) {
+                    while ((unsigned)(v.x >> 32) != tag || (unsigned)(v.y >> 32) != tag) {
                         __nanosleep(32);
                         v = __ldcv(src);
                     }
@@ -662,22 +735,14 @@ k_flow_iter_ws(WsArgs wa)
                         FDN_CHAIN8(d, kk);
                         FDN_DIFFS(d, wb_, wa_);
                         ++kk;
-                        if ((kk & 3) == 0) {   // every 32 columns: let the solve warps follow
-                            __syncwarp(hmask);
-                            __threadfence_block();
-                            if (lane == 0) prog[j & 1] = j * 4096 + 8 * kk;
-                        }
+                        FDN_CHUNK_DONE(kk);
                         if (kk == n8) break;
                         // sets: wb_ = kk, wa_ = kk+1
                         FDN_LOADSET(wb_, kk + 2);
                         FDN_CHAIN8(d, kk);
                         FDN_DIFFS(d, wa_, wb_);
                         ++kk;
-                        if ((kk & 3) == 0) {
-                            __syncwarp(hmask);
-                            __threadfence_block();
-                            if (lane == 0) prog[j & 1] = j * 4096 + 8 * kk;
-                        }
+                        FDN_CHUNK_DONE(kk);
                     }
                     if (ncols & 4) {   // d[0..3] are the differences of the last 4 columns
                         double2 s0, s1;
@@ -689,45 +754,62 @@ k_flow_iter_ws(WsArgs wa)
 #undef FDN_LOADSET
 #undef FDN_DIFFS
 #undef FDN_CHAIN8
-                if (k + 1 < a.strips) {
+#undef FDN_CHUNK_DONE
+                if (k + 1 < wa.strips) {
                     ulonglong2 o;
-                    const unsigned long long tg = (unsigned long long)wa.tag << 32;
+                    const unsigned long long tg = (unsigned long long)tag << 32;
                     o.x = tg | (unsigned)__double2loint(S);
                     o.y = tg | (unsigned)__double2hiint(S);
                     __stcg(pk_out + (int64_t)y * 5 + c, o);
                 }
             }
             __syncwarp();
-            __threadfence_block();
-            if (lane == 0) prog[j & 1] = j * 4096 + 4095;   // the whole tile is scanned
+            if (lane == 0) mbar_arrive(bars + 8 * ((ncols - 1) >> 5));   // the last chunk: the whole tile is scanned
         }
+        warp_exit();
         return;
     }
 
-    // =============================== column warps: phases V and S ===============================
+    // =============================== column warps: phase V ===============================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 176;");
-    // phase V: thread t <-> tile position t <-> image column x0 - m - 1 + t (clamped: replicated border); threads
-    // beyond the strip's halo work on a clamped column too, their results are never read
+    // thread t <-> tile position t <-> image column x0 - m - 1 + t (clamped: replicated border); threads beyond the
+    // strip's halo work on a clamped column too, their results are never read
     const int xcl = min(max(x0 - m - 1 + t, 0), w - 1);
     const float sxc = __fmul_rn(xcl < 5 ? (xcl < 2 ? 0.14f : 0.4472f) : 1.f,
                                 xcl >= w - 5 ? (w - xcl - 1 < 2 ? 0.14f : 0.4472f) : 1.f);
 
-    const float* R0 = a.R + (int64_t)a.map0.slot(b) * a.R_stride;
-    const float* R1 = a.R + (int64_t)a.map1.slot(b) * a.R_stride;
+    const float* R0 = wa.R + (int64_t)wa.map0.slot(b) * wa.R_stride;
+    const float* R1 = wa.R + (int64_t)wa.map1.slot(b) * wa.R_stride;
     const float4* R0a = reinterpret_cast<const float4*>(R0);
     const float* R0b = R0 + (int64_t)4 * h * w;
     const float4* R1a = reinterpret_cast<const float4*>(R1);
     const float* R1b = R1 + (int64_t)4 * h * w;
-    const float2* fin = reinterpret_cast<const float2*>(a.flow_in) + (int64_t)b * h * w;
+    const float2* fin = reinterpret_cast<const float2*>(wa.fin[it]) + (int64_t)b * h * w;
 
-    // R0 / flow of one row of this thread's column: read once, streamed past L1's resident R1 rows
+    // R0 / flow of one row of this thread's column: read once, streamed past L1's resident R1 rows. The flow may
+    // have been written by another SM earlier in this launch (previous iteration): L2 is the point of coherence.
     auto load_row = [&](int y) {
         RowIn in;
         const int idx = min(y, h - 1) * w + xcl;
-        asm("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(in.f.x), "=f"(in.f.y) : "l"(fin + idx));
+        asm volatile("ld.global.cg.v2.f32 {%0, %1}, [%2];" : "=f"(in.f.x), "=f"(in.f.y) : "l"(fin + idx));
         asm("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
                      : "=f"(in.c03.x), "=f"(in.c03.y), "=f"(in.c03.z), "=f"(in.c03.w) : "l"(R0a + idx));
         asm("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(in.c4) : "l"(R0b + idx));
+#if FDN_WS_L2PF
+        // The six scoreboard slots of a warp are shared between these loads and the R1 gathers: a gather's first use
+        // also waits for every streaming load in flight on the same slot. Bring the row into L2 FDN_WS_L2PF tiles
+        // before it is loaded (prefetches take no scoreboard slot), so that what a gather may wait for is an L2 hit.
+        const int idp = min(y + (FDN_WS_L2PF > 0 ? FDN_WS_L2PF : -FDN_WS_L2PF) * TR, h - 1) * w + xcl;
+#if FDN_WS_L2PF > 0
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(fin + idp));
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(R0a + idp));
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(R0b + idp));
+#else
+        asm volatile("prefetch.global.L1 [%0];" :: "l"(fin + idp));
+        asm volatile("prefetch.global.L1 [%0];" :: "l"(R0a + idp));
+        asm volatile("prefetch.global.L1 [%0];" :: "l"(R0b + idp));
+#endif
+#endif
         return in;
     };
 
@@ -801,16 +883,33 @@ k_flow_iter_ws(WsArgs wa)
             // R0 / flow of the same rows of the NEXT tile: in flight for a whole tile period
 #pragma unroll
             for (int rr = 0; rr < SR; rr++) cur[half * SR + rr] = load_row(y0 + TR + half * SR + rr + m);
+#ifdef FDN_WS_MIDFENCE
+            if (half == 0) __threadfence_block();
+#endif
         }
+#ifndef FDN_WS_NOFENCE
         __threadfence_block();
+#endif
         nbar_arrive(BAR_FULL + (j & 1), NT + 32);          // the scan warp may start on tile j
     }
+    warp_exit();
 }
 
-static unsigned long long g_flow_epoch = 1;
+static std::atomic<unsigned long long> g_flow_epoch{1};
+static std::atomic<int> g_flow_variant{1};
+void set_flow_iter_variant(int v) { g_flow_variant.store(v ? 1 : 0); }
 #define FDN_MAX_STRIPS 64
 
 static int strip_width(int w) { return w > 96 ? 128 : 32; }   // k_flow_iter
+
+// packet tags of one k_flow_iter_ws launch: cnt consecutive 32-bit values, none of them 0
+static unsigned next_packet_tags(int cnt)
+{
+    for (;;) {
+        const unsigned lo = (unsigned)g_flow_epoch.fetch_add((unsigned long long)cnt);
+        if (lo != 0 && lo <= 0xffffffffu - (unsigned)cnt) return lo;
+    }
+}
 
 // strips of k_flow_iter_ws: CW = multiple of 4, <= WsCfg::CWMAX
 static int ws_strip_width(int w, int cwmax)
@@ -822,69 +921,79 @@ static int ws_strip_width(int w, int cwmax)
 typedef WsCfg<2, FDN_WS_NT> WsCfg2;
 
 static size_t align256(size_t v) { return (v + 255) / 256 * 256; }
-static size_t flow_flag_bytes(int n) { return align256(sizeof(unsigned long long) * (size_t)n * FDN_MAX_STRIPS); }
-static const size_t kFlowTicketBytes = 256;   // k_flow_iter_ws: ticket counters
-static size_t flow_carry_bytes(int n, int h, int w)   // k_flow_iter: one double per (pair, strip, row, channel)
+
+// Scratch layout (offsets depend on the capacity only, see FlowScratch):
+//   [ctl: tickets taken, warps / blocks finished]                                    256 B, zero between launches
+//   [done: FDN_WS_MAX_ITERS x cap_n counters of k_flow_iter_ws]                       zero between launches
+//   [flags: cap_n x FDN_MAX_STRIPS epochs of k_flow_iter]                             only ever grow
+//   [packets of k_flow_iter_ws: cap_n x strips x H x 5 tagged 16-byte pairs]
+//   [carries of k_flow_iter:    cap_n x strips x H x 5 doubles]
+// The two carry areas are disjoint, so a level run by one kernel never writes where the other kernel polls at
+// another level (a plain double must never be mistaken for a tagged packet). A smaller launch (coarser level, last
+// chunk of a pass) uses a prefix of each area.
+int flow_scratch_make(void* scratch, size_t bytes, int cap_n, int H, int W, FlowScratch* fs)
 {
-    return align256(sizeof(double) * 5 * (size_t)n * (size_t)cdiv(w, strip_width(w)) * h);
-}
-static size_t flow_packet_bytes(int n, int h, int w)  // k_flow_iter_ws: one 16-byte packet pair per carry
-{
-    const size_t strips = (size_t)cdiv(w, ws_strip_width(w, WsCfg2::CWMAX));
-    return align256(sizeof(ulonglong2) * 5 * (size_t)n * strips * h);
+    fs->base = static_cast<char*>(scratch);
+    fs->bytes = bytes;
+    fs->cap_n = cap_n; fs->H = H; fs->W = W;
+    size_t off = 256;
+    fs->off_done = off;    off += align256(sizeof(unsigned) * FDN_WS_MAX_ITERS * (size_t)cap_n);
+    fs->off_flags = off;   off += align256(sizeof(unsigned long long) * (size_t)cap_n * FDN_MAX_STRIPS);
+    fs->off_packets = off;
+    off += align256(sizeof(ulonglong2) * 5 * (size_t)cap_n * (size_t)cdiv(W, ws_strip_width(W, WsCfg2::CWMAX)) * H);
+    fs->off_carry = off;
+    off += align256(sizeof(double) * 5 * (size_t)cap_n * (size_t)cdiv(W, strip_width(W)) * H);
+    if (scratch && bytes < off) {
+        set_error("flow iteration scratch too small: need %zu bytes, got %zu", off, bytes);
+        return FDN_ERR_WORKSPACE;
+    }
+    fs->bytes = off;
+    return FDN_OK;
 }
 
-// Scratch layout: [flags: n * MAX_STRIPS u64][tickets of k_flow_iter_ws][packets of k_flow_iter_ws ...  ... carries of
-// k_flow_iter]. The flag
-// area has the same place and size for every pyramid level that shares the scratch (it only ever holds epochs of
-// earlier launches, which compare below the current one). Packets grow from the front and plain carries sit at the
-// END of the scratch, so a level run by one kernel never writes into the area the other kernel polls at another
-// level (a plain double must never be mistaken for a tagged packet). Both are rewritten by a launch before it
-// reads them.
-size_t flow_iter_scratch_bytes(int n, int h, int w)
+size_t flow_iter_scratch_bytes(int cap_n, int H, int W)
 {
-    return flow_flag_bytes(n) + kFlowTicketBytes + flow_packet_bytes(n, h, w) + flow_carry_bytes(n, h, w);
+    FlowScratch fs;
+    flow_scratch_make(nullptr, 0, cap_n, H, W, &fs);
+    return fs.bytes;
 }
 
-int flow_iter_scratch_init(void* scratch, size_t bytes, cudaStream_t st)
+int flow_iter_scratch_init(const FlowScratch& fs, cudaStream_t st)
 {
-    // flags must start below every epoch; carries need no initialisation
-    FDN_CUDA(cudaMemsetAsync(scratch, 0, bytes, st));
+    // counters and flags must start at zero; carries / packets need no initialisation but a stale bit pattern must
+    // not look like a packet of a future launch: zero everything once per pass
+    FDN_CUDA(cudaMemsetAsync(fs.base, 0, fs.bytes, st));
     return FDN_OK;
 }
 
 // function attributes are per device: remember which devices of this process have them
-static bool first_use_on_device(bool (&seen)[64])
+static bool first_use_on_device(std::atomic<bool> (&seen)[64])
 {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
-    if (seen[dev]) return false;
-    seen[dev] = true;
-    return true;
+    return !seen[dev].exchange(true);
 }
 
 template <int CW, int TR, int MT, int MINB>
-static int launch_flow_variant(const FlowIterArgs& a, dim3 grid, size_t smem, cudaStream_t st)
+static int launch_flow_variant(const FlowIterArgs& a, unsigned blocks, size_t smem, cudaStream_t st)
 {
-    static bool seen[64] = {};
+    static std::atomic<bool> seen[64];
     if (first_use_on_device(seen))
         FDN_CUDA(cudaFuncSetAttribute(k_flow_iter<CW, TR, MT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       200 * 1024));
-    k_flow_iter<CW, TR, MT, MINB><<<grid, CW + 32, smem, st>>>(a);
+    k_flow_iter<CW, TR, MT, MINB><<<blocks, CW + 32, smem, st>>>(a);
     return FDN_OK;
 }
 
-int launch_flow_iter(const float* R, int64_t R_stride, SlotMap map0, SlotMap map1, const float* flow_in,
-                     float* flow_out, int n, int h, int w, int winsize, void* scratch, size_t scratch_bytes,
-                     cudaStream_t st)
+// one iteration with the strip kernel
+static int launch_flow_iter_strip(const float* R, int64_t R_stride, SlotMap map0, SlotMap map1, const float* flow_in,
+                                  float* flow_out, int n, int h, int w, int winsize, const FlowScratch& fs,
+                                  cudaStream_t st)
 {
-    FDN_CHECK_ARG(winsize >= 1 && winsize <= 31, "winsize %d unsupported (1..31)", winsize);
-    FDN_CHECK_ARG(flow_in != flow_out, "flow_in and flow_out must not alias");
-    FDN_CHECK_ARG((int64_t)h * w < (1ll << 28), "level image too large");
-    FDN_CHECK_ARG(scratch && scratch_bytes >= flow_iter_scratch_bytes(n, h, w), "flow iteration scratch too small");
     FlowIterArgs a;
     a.R = R; a.R_stride = R_stride;
     a.h = h; a.w = w; a.m = winsize / 2;
+    a.n = n;
     a.scale = 1. / ((double)winsize * winsize);
     const int m = a.m;
     const int RR = 2 * m + 2;
@@ -895,86 +1004,105 @@ int launch_flow_iter(const float* R, int64_t R_stride, SlotMap map0, SlotMap map
     const int TR = (wide && m == 2) ? 6 : 4;
     a.strips = (int)cdiv(w, CW);
     a.LS = tile_line_stride(CW, m);
-    // see flow_iter_scratch_bytes for the layout; a smaller level fits into the level-0 scratch
     FDN_CHECK_ARG(a.strips <= FDN_MAX_STRIPS, "image too wide (%d strips)", a.strips);
-    a.flags = static_cast<unsigned long long*>(scratch);
-    a.carry = reinterpret_cast<double*>(static_cast<char*>(scratch) + scratch_bytes - flow_carry_bytes(n, h, w));
+    a.ctl = reinterpret_cast<unsigned*>(fs.base);
+    a.flags = reinterpret_cast<unsigned long long*>(fs.base + fs.off_flags);
+    a.carry = reinterpret_cast<double*>(fs.base + fs.off_carry);
     const size_t smem = sizeof(double) * TR * 5 * a.LS + sizeof(float) * RR * 5 * NT;
     const unsigned long long tiles = (unsigned long long)cdiv(h, TR);
-    // warp-specialised variant (default for winsize 5 on images that are not tiny); FDN_FLOW_ITER=old keeps k_flow_iter
-    const char* env_variant = getenv("FDN_FLOW_ITER");   // read per launch: tests flip it to compare both kernels
-    const int variant = (env_variant && strcmp(env_variant, "old") == 0) ? 0 : 1;
-    const bool win = variant == 1 && m == 2 && w % 4 == 0 && w >= 64 && h >= 16 &&
+    a.map0 = map0; a.map1 = map1;
+    a.flow_in = flow_in; a.flow_out = flow_out;
+    a.epoch = g_flow_epoch.fetch_add(tiles + 1);
+    ProfScope ps(K_FLOW_ITER, 56.0 * n * h * w, st);
+    const unsigned blocks = (unsigned)a.strips * (unsigned)n;
+    int rc;
+    if (wide) {
+        if (m == 2) rc = launch_flow_variant<128, 6, 2, 4>(a, blocks, smem, st);
+        else if (m == 4) rc = launch_flow_variant<128, 4, 4, 4>(a, blocks, smem, st);
+        else rc = launch_flow_variant<128, 4, 0, 4>(a, blocks, smem, st);
+    } else {
+        if (m == 2) rc = launch_flow_variant<32, 4, 2, 8>(a, blocks, smem, st);
+        else rc = launch_flow_variant<32, 4, 0, 8>(a, blocks, smem, st);
+    }
+    if (rc) return rc;
+    FDN_LAUNCHED("k_flow_iter");
+    return FDN_OK;
+}
+
+int launch_flow_level(const float* R, int64_t R_stride, SlotMap map0, SlotMap map1, float* cur, float* bufa, float* bufb,
+                      int n, int h, int w, int winsize, int iters, const FlowScratch& fs, cudaStream_t st,
+                      float** result)
+{
+    FDN_CHECK_ARG(winsize >= 1 && winsize <= 31, "winsize %d unsupported (1..31)", winsize);
+    FDN_CHECK_ARG(cur != bufa && cur != bufb && bufa != bufb, "the three flow buffers must be distinct");
+    FDN_CHECK_ARG((int64_t)h * w < (1ll << 28), "level image too large");
+    FDN_CHECK_ARG(n >= 1 && n <= fs.cap_n && h <= fs.H && w <= fs.W, "flow iteration scratch was sized for %d pairs of %d x %d",
+                  fs.cap_n, fs.H, fs.W);
+    FDN_CHECK_ARG((int64_t)n * FDN_MAX_STRIPS * FDN_WS_MAX_ITERS < (1ll << 31), "too many image pairs in one launch");
+    float* bufs[3] = {cur, bufa, bufb};
+    const int m = winsize / 2;
+    // warp-specialised variant (default for winsize 5 on images that are not tiny)
+    const bool win = g_flow_variant.load() == 1 && m == 2 && w % 4 == 0 && w >= 64 && h >= 16 &&
                      (reinterpret_cast<uintptr_t>(R) & 15) == 0 && R_stride % 4 == 0;
-    if (win) {
-        WsArgs wa;
-        wa.CW = ws_strip_width(w, WsCfg2::CWMAX);
-        a.strips = (int)cdiv(w, wa.CW);
-        FDN_CHECK_ARG(a.strips <= FDN_MAX_STRIPS, "image too wide (%d strips)", a.strips);
-        wa.ticket = reinterpret_cast<unsigned*>(static_cast<char*>(scratch) + flow_flag_bytes(n));
-        wa.packets = reinterpret_cast<ulonglong2*>(static_cast<char*>(scratch) + flow_flag_bytes(n) + kFlowTicketBytes);
-        static bool seen[64] = {};
-        if (first_use_on_device(seen)) {
-            FDN_CUDA(cudaFuncSetAttribute(k_flow_iter_ws<2, FDN_WS_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)WsCfg2::smem_bytes));
-            // leave the rest of the SM's L1/shared array to L1: the R1 rows a strip walks over live there
-            FDN_CUDA(cudaFuncSetAttribute(k_flow_iter_ws<2, FDN_WS_NT>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                          (int)((2 * (WsCfg2::smem_bytes + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024))));
-            if (getenv("FDN_DEBUG")) {
-                int nb = 0;
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_flow_iter_ws<2, FDN_WS_NT>, FDN_WS_NT + 128,
-                                                              WsCfg2::smem_bytes);
-                fprintf(stderr, "[fdn] k_flow_iter_ws: %d blocks/SM, %zu B shared memory per block\n", nb,
-                        (size_t)WsCfg2::smem_bytes);
-            }
+    if (!win) {
+        for (int i = 0; i < iters; i++) {
+            int rc = launch_flow_iter_strip(R, R_stride, map0, map1, bufs[i % 3], bufs[(i + 1) % 3], n, h, w, winsize, fs,
+                                            st);
+            if (rc) return rc;
         }
-        if ((unsigned)g_flow_epoch == 0) g_flow_epoch++;   // the packet tag is the low word of the epoch, never 0
-        wa.tag = (unsigned)g_flow_epoch;
-        wa.exp = 0;
-#ifdef FDN_WS_EXPERIMENTS   // phase-removal timing experiments of tools/flow_iter_lab.py (FDN_EXP bit mask): wrong results
-        { const char* e = getenv("FDN_EXP"); wa.exp = e ? atoi(e) : 0; }
-#endif
-        for (int b0 = 0; b0 < n; b0 += 65535) {
-            const int nb = n - b0 < 65535 ? n - b0 : 65535;
-            a.map0 = map0; a.map0.base += b0;
-            a.map1 = map1; a.map1.base += b0;
-            a.flow_in = flow_in + (int64_t)b0 * h * w * 2;
-            a.flow_out = flow_out + (int64_t)b0 * h * w * 2;
-            a.epoch = g_flow_epoch;
-            wa.a = a;
-            ProfScope ps(K_FLOW_ITER, 56.0 * nb * h * w, st);
-            dim3 grid((unsigned)a.strips, (unsigned)nb);
-            k_flow_iter_ws<2, FDN_WS_NT><<<grid, FDN_WS_NT + 128, WsCfg2::smem_bytes, st>>>(wa);
-            FDN_LAUNCHED("k_flow_iter_ws");
-            wa.packets += (int64_t)nb * a.strips * h * 5;
-        }
-        g_flow_epoch += tiles + 1;
+        *result = bufs[iters % 3];
         return FDN_OK;
     }
-    for (int b0 = 0; b0 < n; b0 += 65535) {
-        const int nb = n - b0 < 65535 ? n - b0 : 65535;
-        a.map0 = map0; a.map0.base += b0;
-        a.map1 = map1; a.map1.base += b0;
-        a.flow_in = flow_in + (int64_t)b0 * h * w * 2;
-        a.flow_out = flow_out + (int64_t)b0 * h * w * 2;
-        a.epoch = g_flow_epoch;
-        ProfScope ps(K_FLOW_ITER, 56.0 * nb * h * w, st);
-        dim3 grid((unsigned)a.strips, (unsigned)nb);
-        int rc;
-        if (wide) {
-            if (m == 2) rc = launch_flow_variant<128, 6, 2, 4>(a, grid, smem, st);
-            else if (m == 4) rc = launch_flow_variant<128, 4, 4, 4>(a, grid, smem, st);
-            else rc = launch_flow_variant<128, 4, 0, 4>(a, grid, smem, st);
-        } else {
-            if (m == 2) rc = launch_flow_variant<32, 4, 2, 8>(a, grid, smem, st);
-            else rc = launch_flow_variant<32, 4, 0, 8>(a, grid, smem, st);
+    WsArgs wa;
+    wa.R = R; wa.R_stride = R_stride;
+    wa.map0 = map0; wa.map1 = map1;
+    wa.n = n; wa.h = h; wa.w = w;
+    wa.scale = 1. / ((double)winsize * winsize);
+    wa.CW = ws_strip_width(w, WsCfg2::CWMAX);
+    wa.strips = (int)cdiv(w, wa.CW);
+    FDN_CHECK_ARG(wa.strips <= FDN_MAX_STRIPS, "image too wide (%d strips)", wa.strips);
+    wa.ctl = reinterpret_cast<unsigned*>(fs.base);
+    wa.done = reinterpret_cast<unsigned*>(fs.base + fs.off_done);
+    wa.packets = reinterpret_cast<ulonglong2*>(fs.base + fs.off_packets);
+    static std::atomic<bool> seen[64];
+    if (first_use_on_device(seen)) {
+        FDN_CUDA(cudaFuncSetAttribute(k_flow_iter_ws<2, FDN_WS_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)WsCfg2::smem_bytes));
+        // leave the rest of the SM's L1/shared array to L1: the R1 rows a strip walks over live there
+        FDN_CUDA(cudaFuncSetAttribute(k_flow_iter_ws<2, FDN_WS_NT>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                      (int)((2 * (WsCfg2::smem_bytes + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024))));
+        if (getenv("FDN_DEBUG")) {
+            int nb = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_flow_iter_ws<2, FDN_WS_NT>, FDN_WS_NT + 128,
+                                                          WsCfg2::smem_bytes);
+            fprintf(stderr, "[fdn] k_flow_iter_ws: %d blocks/SM, %zu B shared memory per block\n", nb,
+                    (size_t)WsCfg2::smem_bytes);
         }
-        if (rc) return rc;
-        FDN_LAUNCHED("k_flow_iter");
-        a.carry += (int64_t)nb * a.strips * h * 5;
-        a.flags += (int64_t)nb * a.strips;
     }
-    g_flow_epoch += tiles + 1;
+    wa.exp = 0;
+#ifdef FDN_WS_EXPERIMENTS   // phase-removal timing experiments of tools/flow_iter_lab.py (FDN_EXP bit mask): wrong results
+    { const char* e = getenv("FDN_EXP"); wa.exp = e ? atoi(e) : 0; }
+#endif
+#ifdef FDN_WS_ITERS_PER_LAUNCH
+    const int per_launch = FDN_WS_ITERS_PER_LAUNCH;
+#else
+    const int per_launch = FDN_WS_MAX_ITERS;
+#endif
+    for (int i0 = 0; i0 < iters; i0 += per_launch) {
+        const int cnt = iters - i0 < per_launch ? iters - i0 : per_launch;
+        for (int i = 0; i < cnt; i++) {
+            wa.fin[i] = bufs[(i0 + i) % 3];
+            wa.fout[i] = bufs[(i0 + i + 1) % 3];
+        }
+        for (int i = cnt; i < FDN_WS_MAX_ITERS; i++) { wa.fin[i] = nullptr; wa.fout[i] = nullptr; }
+        wa.iters = cnt;
+        wa.tag = next_packet_tags(cnt);
+        ProfScope ps(K_FLOW_ITER, 56.0 * cnt * n * h * w, st);
+        const unsigned blocks = (unsigned)cnt * (unsigned)n * (unsigned)wa.strips;
+        k_flow_iter_ws<2, FDN_WS_NT><<<blocks, FDN_WS_NT + 128, WsCfg2::smem_bytes, st>>>(wa);
+        FDN_LAUNCHED("k_flow_iter_ws");
+    }
+    *result = bufs[iters % 3];
     return FDN_OK;
 }
 

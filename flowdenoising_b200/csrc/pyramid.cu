@@ -432,20 +432,6 @@ k_polyexp(const float* __restrict__ img, int64_t img_stride, float* __restrict__
 #define PBX_MAX ((PL + PT + PN_MAX + 3) & ~3)
 #define PBY_MAX (PT + 2 * PN_MAX)
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
-{
-    uint32_t done = 0;
-    while (!done) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    }
-}
-
 // one thread arms the mbarrier with the byte count and starts the 3-D bulk tensor copy (box -> shared memory)
 __device__ __forceinline__ void tma_load_box(uint64_t tmap_addr, uint32_t dst, uint32_t bar, uint32_t bytes, int cx,
                                              int cy, int cz)

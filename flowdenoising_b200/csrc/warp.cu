@@ -51,7 +51,7 @@ k_warp_acc(const float* __restrict__ neigh, int64_t n_ss, int64_t n_rs, SlotMap 
     }
     float* ap = acc + (int64_t)b * a_ss + (int64_t)y * a_rs + x;
     const double prod = __dmul_rn((double)v, weight);
-    *ap = first ? (float)prod : (float)__dadd_rn((double)*ap, prod);
+    *ap = (float)__dadd_rn(first ? 0.0 : (double)*ap, prod);   // tmp = zeros; tmp += v * k (:308, :316)
 }
 
 // Four consecutive pixels per thread (128-bit flow / accumulator accesses, four independent gathers in flight).
@@ -101,7 +101,7 @@ k_warp_acc4(const float* __restrict__ neigh, int64_t n_ss, int64_t n_rs, SlotMap
     float o[4];
     if (first) {
 #pragma unroll
-        for (int i = 0; i < 4; i++) o[i] = (float)__dmul_rn((double)v[i], weight);
+        for (int i = 0; i < 4; i++) o[i] = (float)__dadd_rn(0.0, __dmul_rn((double)v[i], weight));   // tmp = zeros; tmp += v * k
     } else {
         const float4 a = *ap;
         const float av[4] = {a.x, a.y, a.z, a.w};
@@ -141,6 +141,161 @@ int launch_warp_acc(const float* neigh, int64_t n_ss, int64_t n_rs, SlotMap n_ma
                                          flow ? reinterpret_cast<const float2*>(flow) + (int64_t)b0 * H * W : nullptr,
                                          weight, acc + (int64_t)b0 * a_ss, a_ss, a_rs, H, W, first);
         FDN_LAUNCHED("k_warp_acc");
+    }
+    return FDN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Both chain directions in one launch (the two chains of src/flowdenoising.py:311-316 and :319-324 advance together):
+// images [0, n) are the backward neighbours -- remapped and accumulated in place, the reference's order -- and images
+// [n, 2n) the forward neighbours, whose remapped values wait in `stash` until the backward chain and the centre tap
+// are in the accumulator (k_acc_finish applies them in the reference's order: centre, +1, ..., +r).
+// ------------------------------------------------------------------------------------------------
+template <int VEC>
+__global__ void __launch_bounds__(128)
+k_warp_pair(const float* __restrict__ neigh, int64_t n_ss, int64_t n_rs, SlotMap n_map, const float* __restrict__ flow,
+            double weight, float* __restrict__ acc, int64_t a_ss, int64_t a_rs, float* __restrict__ stash, int n, int b0,
+            int H, int W, int first)
+{
+    const int x = (blockIdx.x * 128 + threadIdx.x) * VEC;
+    const int y = blockIdx.y;
+    const int b = b0 + blockIdx.z;   // 0 .. 2n-1
+    if (x >= W) return;
+    const float* src = neigh + (int64_t)n_map.slot(b) * n_ss;
+    const int64_t fpx = ((int64_t)b * H + y) * W + x;
+    float v[VEC];
+    if (VEC == 4) {
+        const float4* fp = reinterpret_cast<const float4*>(flow) + fpx / 2;   // two float2 flows per float4
+        const float4 f01 = __ldg(fp), f23 = __ldg(fp + 1);
+        v[0] = remap_px(src, n_rs, f01.x, f01.y, x, y, H, W);
+        v[1 % VEC] = remap_px(src, n_rs, f01.z, f01.w, x + 1, y, H, W);
+        v[2 % VEC] = remap_px(src, n_rs, f23.x, f23.y, x + 2, y, H, W);
+        v[3 % VEC] = remap_px(src, n_rs, f23.z, f23.w, x + 3, y, H, W);
+    } else {
+        const float2 f = __ldg(reinterpret_cast<const float2*>(flow) + fpx);
+        v[0] = remap_px(src, n_rs, f.x, f.y, x, y, H, W);
+    }
+    if (b < n) {
+        float* ap = acc + (int64_t)b * a_ss + (int64_t)y * a_rs + x;
+        if (VEC == 4) {
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!first) a = *reinterpret_cast<float4*>(ap);
+            const float av[4] = {a.x, a.y, a.z, a.w};
+            float o[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                o[i] = (float)__dadd_rn(first ? 0.0 : (double)av[i], __dmul_rn((double)v[i % VEC], weight));
+            *reinterpret_cast<float4*>(ap) = make_float4(o[0], o[1], o[2], o[3]);
+        } else {
+            *ap = (float)__dadd_rn(first ? 0.0 : (double)*ap, __dmul_rn((double)v[0], weight));
+        }
+    } else {
+        float* sp = stash + ((int64_t)(b - n) * H + y) * W + x;
+        if (VEC == 4) *reinterpret_cast<float4*>(sp) = make_float4(v[0], v[1 % VEC], v[2 % VEC], v[3 % VEC]);
+        else *sp = v[0];
+    }
+}
+
+int launch_warp_pair(const float* neigh, int64_t n_ss, int64_t n_rs, SlotMap n_map, const float* flow, double weight,
+                     float* acc, int64_t a_ss, int64_t a_rs, float* stash, int n, int H, int W, int first,
+                     cudaStream_t st)
+{
+    const bool vec4 = W % 4 == 0 && n_ss % 4 == 0 && n_rs % 4 == 0 && a_ss % 4 == 0 && a_rs % 4 == 0 &&
+                      (reinterpret_cast<uintptr_t>(neigh) & 15) == 0 && (reinterpret_cast<uintptr_t>(acc) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(flow) & 15) == 0 && (reinterpret_cast<uintptr_t>(stash) & 15) == 0;
+    FDN_CHECK_ARG(H <= 65535, "image too tall for one launch");
+    for (int b0 = 0; b0 < 2 * n; b0 += 65535) {
+        const int nb = 2 * n - b0 < 65535 ? 2 * n - b0 : 65535;
+        // remap: flow 8 + neighbour 4; backward half: accumulator 4 (+4 unless first), forward half: stash 4
+        ProfScope ps(K_WARP_ACC, (double)nb * H * W * (12.0 + (first ? 4.0 : 6.0)), st);
+        if (vec4) {
+            dim3 grid((unsigned)cdiv(W, 512), (unsigned)H, (unsigned)nb);
+            k_warp_pair<4><<<grid, 128, 0, st>>>(neigh, n_ss, n_rs, n_map, flow, weight, acc, a_ss, a_rs, stash, n, b0, H, W,
+                                                 first);
+        } else {
+            dim3 grid((unsigned)cdiv(W, 128), (unsigned)H, (unsigned)nb);
+            k_warp_pair<1><<<grid, 128, 0, st>>>(neigh, n_ss, n_rs, n_map, flow, weight, acc, a_ss, a_rs, stash, n, b0, H, W,
+                                                 first);
+        }
+        FDN_LAUNCHED("k_warp_pair");
+    }
+    return FDN_OK;
+}
+
+#define FDN_MAX_R 128
+struct FinishTaps {
+    double k[FDN_MAX_R + 1];   // centre, +1, ..., +r
+};
+
+template <int VEC>
+__global__ void __launch_bounds__(128)
+k_acc_finish(const float* __restrict__ centre, int64_t c_ss, int64_t c_rs, SlotMap c_map, const float* __restrict__ stash,
+             int64_t stash_stride, int r, FinishTaps taps, float* __restrict__ acc, int64_t a_ss, int64_t a_rs, int b0,
+             int H, int W, int have_acc)
+{
+    const int x = (blockIdx.x * 128 + threadIdx.x) * VEC;
+    const int y = blockIdx.y;
+    const int b = b0 + blockIdx.z;
+    if (x >= W) return;
+    const float* cp = centre + (int64_t)c_map.slot(b) * c_ss + (int64_t)y * c_rs + x;
+    float* ap = acc + (int64_t)b * a_ss + (int64_t)y * a_rs + x;
+    const float* sp = stash + ((int64_t)b * H + y) * W + x;
+    float a[VEC], v[VEC];
+    auto load = [&](const float* p, float* dst) {
+        if (VEC == 4) {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(p));
+            dst[0] = q.x; dst[1 % VEC] = q.y; dst[2 % VEC] = q.z; dst[3 % VEC] = q.w;
+        } else {
+            dst[0] = __ldg(p);
+        }
+    };
+#pragma unroll
+    for (int i = 0; i < VEC; i++) a[i] = 0.f;
+    if (have_acc) {
+        if (VEC == 4) {
+            const float4 q = *reinterpret_cast<const float4*>(ap);
+            a[0] = q.x; a[1 % VEC] = q.y; a[2 % VEC] = q.z; a[3 % VEC] = q.w;
+        } else {
+            a[0] = *ap;
+        }
+    }
+    load(cp, v);   // tmp_slice += vol[z] * kernel[ks2]  (src/flowdenoising.py:317)
+#pragma unroll
+    for (int i = 0; i < VEC; i++) a[i] = (float)__dadd_rn((double)a[i], __dmul_rn((double)v[i], taps.k[0]));
+    for (int d = 0; d < r; d++) {   // forward chain, nearest neighbour first (:319-324)
+        load(sp + (int64_t)d * stash_stride, v);
+#pragma unroll
+        for (int i = 0; i < VEC; i++) a[i] = (float)__dadd_rn((double)a[i], __dmul_rn((double)v[i], taps.k[d + 1]));
+    }
+    if (VEC == 4) *reinterpret_cast<float4*>(ap) = make_float4(a[0], a[1 % VEC], a[2 % VEC], a[3 % VEC]);
+    else *ap = a[0];
+}
+
+int launch_acc_finish(const float* centre, int64_t c_ss, int64_t c_rs, SlotMap c_map, const float* stash, int r,
+                      const double* k, float* acc, int64_t a_ss, int64_t a_rs, int n, int H, int W, int have_acc,
+                      cudaStream_t st)
+{
+    FDN_CHECK_ARG(r >= 0 && r <= FDN_MAX_R, "kernel radius %d unsupported (<= %d)", r, FDN_MAX_R);
+    FDN_CHECK_ARG(H <= 65535, "image too tall for one launch");
+    FinishTaps taps;
+    for (int i = 0; i <= r; i++) taps.k[i] = k[i];
+    const bool vec4 = W % 4 == 0 && c_ss % 4 == 0 && c_rs % 4 == 0 && a_ss % 4 == 0 && a_rs % 4 == 0 &&
+                      (reinterpret_cast<uintptr_t>(centre) & 15) == 0 && (reinterpret_cast<uintptr_t>(acc) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(stash) & 15) == 0;
+    const int64_t stash_stride = (int64_t)n * H * W;
+    for (int b0 = 0; b0 < n; b0 += 65535) {
+        const int nb = n - b0 < 65535 ? n - b0 : 65535;
+        ProfScope ps(K_WARP_ACC, (double)nb * H * W * (4.0 * (r + 2) + (have_acc ? 4.0 : 0.0)), st);
+        if (vec4) {
+            dim3 grid((unsigned)cdiv(W, 512), (unsigned)H, (unsigned)nb);
+            k_acc_finish<4><<<grid, 128, 0, st>>>(centre, c_ss, c_rs, c_map, stash, stash_stride, r, taps, acc, a_ss, a_rs, b0,
+                                                  H, W, have_acc);
+        } else {
+            dim3 grid((unsigned)cdiv(W, 128), (unsigned)H, (unsigned)nb);
+            k_acc_finish<1><<<grid, 128, 0, st>>>(centre, c_ss, c_rs, c_map, stash, stash_stride, r, taps, acc, a_ss, a_rs, b0,
+                                                  H, W, have_acc);
+        }
+        FDN_LAUNCHED("k_acc_finish");
     }
     return FDN_OK;
 }

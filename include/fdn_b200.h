@@ -137,6 +137,16 @@ int fdn_polyexp(const float* d_img, int n, int h, int w, int poly_n, double poly
 size_t fdn_flow_iteration_scratch_bytes(int n, int h, int w);
 int fdn_flow_iteration(const float* d_R0, const float* d_R1, const float* d_flow_in, float* d_flow_out, int n,
                        int h, int w, int winsize, void* d_scratch, size_t scratch_bytes, void* stream);
+/* `iterations` consecutive displacement-update iterations of one level (the `for i < iterations` loop of
+ * cv2.calcOpticalFlowFarneback, reached from src/flowdenoising.py:69-79). Iteration i reads rotation buffer i % 3 and
+ * writes buffer (i + 1) % 3 of {d_flow, d_tmp1, d_tmp2} (each (n, h, w, 2), distinct); *d_result is the buffer that
+ * holds the last output. Up to three iterations run as ONE launch of the warp-specialised kernel. */
+int fdn_flow_iterations(const float* d_R0, const float* d_R1, float* d_flow, float* d_tmp1, float* d_tmp2, int n,
+                        int h, int w, int winsize, int iterations, void* d_scratch, size_t scratch_bytes,
+                        void* stream, float** d_result);
+/* Development / test switch: 1 (default) = warp-specialised k_flow_iter_ws where it applies, 0 = the strip kernel
+ * k_flow_iter everywhere (the two are compared bit for bit by tests/test_gpu_stages.py). Process-wide. */
+void fdn_set_flow_iter_variant(int variant);
 /* Flow resampling between levels: INTER_AREA down-scale * scale (initial flow, coarsest level) and
  * INTER_LINEAR up-scale * 2 (next finer level). */
 int fdn_flow_area_down(const float* d_flow, int n, int H, int W, float* d_out, int h, int w, float scale,

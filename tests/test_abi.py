@@ -58,10 +58,14 @@ def test_workspace_grows_with_chunk():
     a = lib.fdn_workspace_bytes(C.byref(v), 17, C.byref(p), 8)
     b = lib.fdn_workspace_bytes(C.byref(v), 17, C.byref(p), 0)
     assert 0 < a < b
-    # all 64 slices cached once: R = 64 slots * 5 * (256^2 + 128^2 + 64^2 + 32^2) floats, + 3 flow buffers,
-    # + the carries/flags of the exact horizontal running sum (2 strips of 128 columns per image)
+    # all 64 slices cached once: R = 64 slots * 5 * (256^2 + 128^2 + 64^2 + 32^2) floats; both chain directions advance
+    # together: 3 flow buffers of 2 * 64 pairs; the remapped forward neighbours wait in a stash of r = 8 chunk volumes;
+    # + the scratch of the flow iteration for 128 pairs: ticket / finish counters, 3 * 128 dependency counters, the
+    # flags + carries of the strip kernel (2 strips of 128 columns per image) and the carry packets of the
+    # warp-specialised kernel (3 strips of <= 120 columns, 16 bytes per carry)
     R = 64 * 5 * (256 * 256 + 128 * 128 + 64 * 64 + 32 * 32) * 4
-    carries = 64 * 2 * 256 * 5 * 8 + 64 * 64 * 8
-    # + the carry packets of the warp-specialised kernel (3 strips of <= 120 columns, 16 bytes per carry)
-    packets = 64 * 3 * 256 * 5 * 16 + 256     # + its ticket counters
-    assert b == R + 3 * (64 * 256 * 256 * 2 * 4) + carries + packets
+    flows = 3 * (128 * 256 * 256 * 2 * 4)
+    stash = 8 * 64 * 256 * 256 * 4
+    al = lambda v: (v + 255) // 256 * 256
+    scratch = 256 + al(3 * 128 * 4) + 128 * 64 * 8 + 128 * 3 * 256 * 5 * 16 + 128 * 2 * 256 * 5 * 8
+    assert b == R + flows + stash + scratch

@@ -208,3 +208,90 @@ def test_of_odd_shapes_vs_c_oracle(eng, shape, sigmas, lw):
         ref = O.flow_axis_c(cur, axis, k, levels=lw[0], winsize=lw[1])
         check_of(f"odd {shape} axis {axis}", out.cpu().numpy(), ref)
         cur = ref
+
+
+def test_chunk_remainder_with_mixed_kernels(eng):
+    """the last chunk of a pass is smaller than the others; every scratch offset of the flow
+    iteration must depend on the chunk CAPACITY only. Width 384 mixes both flow-iteration kernels over the pyramid
+    levels (384 / 192 / 96 / 48 px: warp-specialised, then the strip kernel with 2 strips and with 1), chunk = 65 leaves
+    remainders of 1 and 2 output slices."""
+    from flowdenoising_b200.engine import FlowParams
+    p = FlowParams()
+    k = O.get_gaussian_kernel(0.5)      # r = 2: 4 flows per slice keep the test short
+    for Z in (66, 67):
+        vol = O.synthetic_volume((Z, 256, 384), seed=71, noise_sigma=8.0)
+        d_in = dev(vol)
+        full = torch.empty_like(d_in)
+        eng.filter_along_axis(d_in, full, 0, k, p)
+        out = torch.empty_like(d_in)
+        eng.filter_along_axis(d_in, out, 0, k, p, chunk=65)
+        assert torch.equal(out, full), f"Z={Z}"
+    # spot-check the unchunked result against the oracle
+    ref = O.flow_axis_c(vol, 0, k, s0=5, s1=6)
+    assert np.array_equal(full.cpu().numpy()[5], ref[5])
+
+
+def _crop_case(golden, fname, name):
+    g = golden(fname)
+    shape = tuple(int(s) for s in g[f"{name}_shape"])
+    seed, axis, l, w = (int(x) for x in g[f"{name}_params"])
+    noise, sigma = (float(x) for x in g[f"{name}_noise_sigma"])
+    vol = O.synthetic_volume(shape, seed=seed, noise_sigma=noise)
+    assert hashlib.sha256(vol.tobytes()).hexdigest() == str(g[f"{name}_input_sha256"]), "synthetic input differs"
+    return g, vol, axis, sigma, l, w, [int(s) for s in g[f"{name}_slices"]]
+
+
+def _check_crop(g, name, got, axis, slices):
+    for s in slices:
+        o = np.ascontiguousarray(np.take(got, s, axis=axis))
+        crop = g[f"{name}_crop_{s}"]
+        check_of(f"{name} slice {s} (crop)", o[:crop.shape[0], :crop.shape[1]], crop)
+        assert hashlib.sha256(o.tobytes()).hexdigest() == str(g[f"{name}_sha_{s}"]), f"{name} slice {s}: SHA-256 differs"
+
+
+@pytest.mark.parametrize("name", ["z", "y", "x"])
+def test_cfg2_crops_vs_reference(eng, golden, name):
+    """BASELINE.json configs[1] at the BENCHMARKED slice size: 1024 x 1024 (Z pass) and 512 x 1024 (Y / X passes)
+    slices, sigma = 2, Farneback defaults -- output slices of the unmodified reference (oracle/gen_golden_big.py),
+    SHA-256 of the whole slice. k_flow_iter_ws runs 9 strips per image here."""
+    from flowdenoising_b200.engine import FlowParams
+    g, vol, axis, sigma, l, w, slices = _crop_case(golden, "cfg2_crops.npz", name)
+    k = O.get_gaussian_kernel(sigma)
+    d_in = dev(vol)
+    out = torch.empty_like(d_in)
+    eng.filter_along_axis(d_in, out, axis, k, FlowParams(l, w))
+    _check_crop(g, name, out.cpu().numpy(), axis, slices)
+    del out, d_in
+    eng.release_workspace()
+    torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("name", ["z", "y"])
+def test_cfg4_crops_vs_reference(eng, golden, name):
+    """BASELINE.json configs[3] parameters: sigma = (4, 2, 2), levels = 5, winsize = 9, uint8 TIFF stack (cast to
+    float32 at load, src/flowdenoising.py:475), 2048-wide slices: 1024 x 2048 with 6 pyramid levels and a 33-tap Z
+    kernel, 256 x 2048 with 4 levels."""
+    from flowdenoising_b200.engine import FlowParams
+    g, vol, axis, sigma, l, w, slices = _crop_case(golden, "cfg4_crops.npz", name)
+    vol8 = vol.astype(np.uint8)
+    assert np.array_equal(vol8.astype(np.float32), vol)
+    k = O.get_gaussian_kernel(sigma)
+    d_in = torch.from_numpy(vol8).cuda().to(torch.float32)      # the TIFF -> float32 cast, on the device
+    out = torch.empty_like(d_in)
+    # the Z-pass case only needs slice 17: a slab view with an explicit halo keeps the test short
+    if name == "z":
+        from flowdenoising_b200._lib import View
+        r = k.size // 2
+        Z, Y, X = vol.shape
+        s = slices[0]
+        idx = [(z % Z) for z in range(s - r, s + r + 1)]
+        slab = d_in[idx].contiguous()
+        o1 = torch.empty((1, Y, X), dtype=torch.float32, device="cuda")
+        eng.filter_view(slab, o1, View(len(idx), 1, r, 0, Y, X, Y * X, X, Y * X, X), k, FlowParams(l, w))
+        out[s] = o1[0]
+    else:
+        eng.filter_along_axis(d_in, out, axis, k, FlowParams(l, w))
+    _check_crop(g, name, out.cpu().numpy(), axis, slices)
+    del out, d_in
+    eng.release_workspace()
+    torch.cuda.empty_cache()

@@ -131,34 +131,81 @@ def test_flow_iteration(eng, shape, win):
         assert np.array_equal(got[i], ref), f"max|d|={d.max()} bit-equal fraction {np.mean(got[i] == ref)}"
 
 
-@pytest.mark.parametrize("shape,scale", [((96, 256), 1.0), ((130, 372), 6.0), ((64, 64), 3.0)])
-def test_flow_iteration_kernels_agree(eng, shape, scale, monkeypatch):
+def _run_iterations(eng, dR, n, flow, h, w, win, iters, variant, scr, merged):
+    """`iters` chained iterations of one level through the C ABI; merged: fdn_flow_iterations (one launch runs up to
+    three iterations), else one fdn_flow_iteration call per iteration. The scratch is reused without clearing."""
+    lib = eng.lib
+    lib.fdn_set_flow_iter_variant(variant)
+    try:
+        cur = dev(flow)
+        if merged:
+            t1, t2 = torch.empty_like(cur), torch.empty_like(cur)
+            res = C.c_void_p()
+            rc = lib.fdn_flow_iterations(dR[:n].data_ptr(), dR[1:].data_ptr(), cur.data_ptr(), t1.data_ptr(), t2.data_ptr(),
+                                         n, h, w, win, iters, scr.data_ptr(), scr.numel(), None, C.byref(res))
+            assert rc == 0, lib.fdn_last_error()
+            out = {cur.data_ptr(): cur, t1.data_ptr(): t1, t2.data_ptr(): t2}[res.value]
+            return out.cpu().numpy()
+        for _ in range(iters):
+            out = torch.empty_like(cur)
+            rc = lib.fdn_flow_iteration(dR[:n].data_ptr(), dR[1:].data_ptr(), cur.data_ptr(), out.data_ptr(), n, h, w,
+                                        win, scr.data_ptr(), scr.numel(), None)
+            assert rc == 0, lib.fdn_last_error()
+            cur = out
+        return cur.cpu().numpy()
+    finally:
+        lib.fdn_set_flow_iter_variant(1)
+
+
+# (64, 1024) and (32, 2048): 9 and 18 strips of the warp-specialised kernel with h >= 16 (the benchmarked widths)
+@pytest.mark.parametrize("shape,scale,n", [((96, 256), 1.0, 5), ((130, 372), 6.0, 5), ((64, 64), 3.0, 5),
+                                           ((64, 1024), 2.0, 40), ((32, 2048), 4.0, 3), ((50, 1000), 1.0, 2)])
+def test_flow_iteration_kernels_agree(eng, shape, scale, n):
     """The warp-specialised kernel (k_flow_iter_ws, default for winsize 5) and the strip kernel (k_flow_iter, pinned
     against the oracle above) write the same bits, also for flows of many pixels (gathers far from the identity
-    position, out-of-image lookups) and over several chained launches that reuse the scratch without clearing it."""
-    n = 5
+    position, out-of-image lookups), with three iterations merged into one launch (ticketed work items, per-pair
+    dependencies between the iterations) and over chained launches that reuse the scratch without clearing it."""
     h, w = shape
-    imgs = images(shape, n + 1, 21)
-    R = np.stack([O.polyexp(imgs[i]) for i in range(n + 1)])
+    imgs = images(shape, 2, 21)
     rng = np.random.default_rng(22)
+    imgs = np.concatenate([imgs] + [np.clip(imgs[:1] + rng.normal(0, 6, (1,) + shape), 0, 255).astype(np.float32)
+                                    for _ in range(n - 1)])
+    R = np.stack([O.polyexp(imgs[i]) for i in range(n + 1)])
     flow = (rng.standard_normal((n, h, w, 2)) * scale).astype(np.float32)
     flow[1, :, : w // 2] += 7.5        # a coherent drift on half an image
-    flow[2, 5:9, 10:40] = 1e4          # far outside the image
+    flow[2 % n, 5:9, 10:40] = 1e4      # far outside the image
     dR = dev(R_from_oracle_layout(R))
     nscr = eng.lib.fdn_flow_iteration_scratch_bytes(n, h, w)
     scr = torch.zeros(nscr, dtype=torch.uint8, device="cuda")
-    res = {}
-    for variant in ("old", "ws"):
-        monkeypatch.setenv("FDN_FLOW_ITER", variant)
-        cur = dev(flow)
-        for it in range(3):            # chained, like the iterations of a level
-            out = torch.empty_like(cur)
-            rc = eng.lib.fdn_flow_iteration(dR[:n].data_ptr(), dR[1:].data_ptr(), cur.data_ptr(), out.data_ptr(), n, h, w,
-                                            5, scr.data_ptr(), nscr, None)
-            assert rc == 0, eng.lib.fdn_last_error()
-            cur = out
-        res[variant] = cur.cpu().numpy()
-    assert np.array_equal(res["old"].view(np.int32), res["ws"].view(np.int32))
+    ref = _run_iterations(eng, dR, n, flow, h, w, 5, 3, 0, scr, merged=False)
+    for iters, merged in ((3, True), (3, False), (3, True)):
+        got = _run_iterations(eng, dR, n, flow, h, w, 5, iters, 1, scr, merged)
+        assert np.array_equal(ref.view(np.int32), got.view(np.int32)), (iters, merged)
+    # other iteration counts through the merged entry point (4 = 3 + 1 launches, 2, 1) against the strip kernel
+    for iters in (1, 2, 4):
+        a = _run_iterations(eng, dR, n, flow, h, w, 5, iters, 0, scr, merged=True)
+        b = _run_iterations(eng, dR, n, flow, h, w, 5, iters, 1, scr, merged=True)
+        assert np.array_equal(a.view(np.int32), b.view(np.int32)), iters
+
+
+def test_flow_iteration_ws_vs_oracle_wide(eng):
+    """k_flow_iter_ws on 9 strips (64 x 1024) against the oracle itself, not only against the strip kernel."""
+    n, h, w = 2, 64, 1024
+    imgs = images((h, w), 2 * n, 31)
+    R = np.stack([O.polyexp(imgs[i]) for i in range(2 * n)])
+    rng = np.random.default_rng(32)
+    flow = (rng.standard_normal((n, h, w, 2)) * 1.5).astype(np.float32)
+    dR = dev(R_from_oracle_layout(R))
+    out = torch.empty((n, h, w, 2), dtype=torch.float32, device="cuda")
+    nscr = eng.lib.fdn_flow_iteration_scratch_bytes(n, h, w)
+    scr = torch.empty(nscr, dtype=torch.uint8, device="cuda")
+    rc = eng.lib.fdn_flow_iteration(dR[:n].data_ptr(), dR[n:].data_ptr(), dev(flow).data_ptr(), out.data_ptr(), n, h, w,
+                                    5, scr.data_ptr(), nscr, None)
+    assert rc == 0, eng.lib.fdn_last_error()
+    got = out.cpu().numpy()
+    for i in range(n):
+        ref = O.blur_solve(O.update_matrices(R[i], R[n + i], flow[i]), 5)
+        assert np.array_equal(got[i], ref), f"bit-equal fraction {np.mean(got[i] == ref)}"
 
 
 def test_flow_resampling_bit_exact(eng):
