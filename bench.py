@@ -309,6 +309,15 @@ def main():
         _lib.check(lib.fdn_profile_read(i, C.byref(ms), C.byref(n), C.byref(by)))
         if n.value:
             kern[lib.fdn_profile_kernel_name(i).decode()] = {"ms": ms.value, "launches": int(n.value), "bytes": by.value}
+    # the dominant kernel per pyramid-level image size (launch records carry n, h, w)
+    by_level = {}
+    flow_id = [i for i in range(lib.fdn_profile_kernel_count()) if lib.fdn_profile_kernel_name(i) == b"k_flow_iter"][0]
+    for i in range(lib.fdn_profile_record_count()):
+        kid = C.c_int(); rn = C.c_int(); rh = C.c_int(); rw = C.c_int(); ms = C.c_double(); by = C.c_double()
+        _lib.check(lib.fdn_profile_record(i, C.byref(kid), C.byref(rn), C.byref(rh), C.byref(rw), C.byref(ms), C.byref(by)))
+        if kid.value == flow_id:
+            d = by_level.setdefault(f"{rh.value}x{rw.value}", {"ms": 0.0, "bytes": 0.0, "launches": 0})
+            d["ms"] += ms.value; d["bytes"] += by.value; d["launches"] += 1
     lib.fdn_profile_reset()
     peak, peak_src = measured_peak()
     dom = max(kern, key=lambda k: kern[k]["ms"]) if kern else None
@@ -336,7 +345,10 @@ def main():
                     "kernel_ms_per_step": {k: round(v["ms"] / args.steps, 3) for k, v in sorted(kern.items())},
                     # every kernel of the path against the same peak (algorithmic bytes / CUDA-event time)
                     "kernel_frac_of_peak": {k: round(v["bytes"] / (v["ms"] * 1e-3) / 1e9 / peak, 3)
-                                            for k, v in sorted(kern.items()) if v["ms"] > 0}}
+                                            for k, v in sorted(kern.items()) if v["ms"] > 0},
+                    "flow_iter_by_level": {k: {"ms_per_step": round(v["ms"] / args.steps, 2), "launches": v["launches"],
+                                               "frac_of_peak": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9 / peak, 3)}
+                                           for k, v in by_level.items() if v["ms"] > 0}}
     model_b = 24.0 if args.no_of else MODEL_BYTES_PER_VOXEL_CFG2 * (1.0 if shape == (512, 1024, 1024) else float("nan"))
     whole_job_frac = (model_b * nvox / (ms_step * 1e-3) / 1e9) / (world * peak) if model_b == model_b else None
 

@@ -41,6 +41,9 @@ SIGNATURES = {
     "fdn_profile_kernel_count": (C.c_int, []),
     "fdn_profile_kernel_name": (C.c_char_p, [C.c_int]),
     "fdn_profile_read": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(c_i64), C.POINTER(C.c_double)]),
+    "fdn_profile_record_count": (C.c_int, []),
+    "fdn_profile_record": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                     C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "fdn_gaussian_kernel": (C.c_int, [C.c_double, C.POINTER(C.c_double), C.c_int]),
     "fdn_level_geometry": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                      C.POINTER(C.c_int), C.POINTER(C.c_double)]),

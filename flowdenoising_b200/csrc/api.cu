@@ -34,6 +34,7 @@ struct ProfRec {
     cudaEvent_t a, b;
     int id;
     double bytes;
+    int n, h, w;   // batch and image size of the launch (0 where the launcher does not say)
 };
 static std::vector<ProfRec> g_prof;
 static std::vector<cudaEvent_t> g_event_pool;
@@ -53,13 +54,14 @@ static cudaEvent_t get_event()
     return e;
 }
 
-void prof_begin(int id, double bytes, cudaStream_t st)
+void prof_begin(int id, double bytes, cudaStream_t st, int n, int h, int w)
 {
     ProfRec r;
     r.a = get_event();
     r.b = get_event();
     r.id = id;
     r.bytes = bytes;
+    r.n = n; r.h = h; r.w = w;
     cudaEventRecord(r.a, st);
     g_prof.push_back(r);
 }
@@ -343,6 +345,24 @@ int fdn_profile_read(int id, double* total_ms, int64_t* launches, double* algori
     if (total_ms) *total_ms = ms;
     if (launches) *launches = n;
     if (algorithmic_bytes) *algorithmic_bytes = bytes;
+    return FDN_OK;
+}
+
+int fdn_profile_record_count(void) { return (int)g_prof.size(); }
+
+int fdn_profile_record(int i, int* id, int* n, int* h, int* w, double* ms, double* algorithmic_bytes)
+{
+    FDN_CHECK_ARG(i >= 0 && i < (int)g_prof.size(), "bad record index %d", i);
+    ProfRec& r = g_prof[i];
+    FDN_CUDA(cudaEventSynchronize(r.b));
+    float t = 0;
+    FDN_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+    if (id) *id = r.id;
+    if (n) *n = r.n;
+    if (h) *h = r.h;
+    if (w) *w = r.w;
+    if (ms) *ms = t;
+    if (algorithmic_bytes) *algorithmic_bytes = r.bytes;
     return FDN_OK;
 }
 

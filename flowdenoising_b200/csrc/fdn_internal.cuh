@@ -50,12 +50,15 @@ enum KernelId {
     K_GAUSS_AXIS, K_GAUSS_ROWS, K_TRANSPOSE, K_COPY3D, K_COUNT
 };
 extern bool g_prof_on;
-void prof_begin(int id, double algorithmic_bytes, cudaStream_t st);
+void prof_begin(int id, double algorithmic_bytes, cudaStream_t st, int n = 0, int h = 0, int w = 0);
 void prof_end(cudaStream_t st);
 struct ProfScope {
     cudaStream_t st;
     bool on;
-    ProfScope(int id, double bytes, cudaStream_t s) : st(s), on(g_prof_on) { if (on) prof_begin(id, bytes, s); }
+    ProfScope(int id, double bytes, cudaStream_t s, int n = 0, int h = 0, int w = 0) : st(s), on(g_prof_on)
+    {
+        if (on) prof_begin(id, bytes, s, n, h, w);
+    }
     ~ProfScope() { if (on) prof_end(st); }
 };
 

@@ -1013,7 +1013,7 @@ static int launch_flow_iter_strip(const float* R, int64_t R_stride, SlotMap map0
     a.map0 = map0; a.map1 = map1;
     a.flow_in = flow_in; a.flow_out = flow_out;
     a.epoch = g_flow_epoch.fetch_add(tiles + 1);
-    ProfScope ps(K_FLOW_ITER, 56.0 * n * h * w, st);
+    ProfScope ps(K_FLOW_ITER, 56.0 * n * h * w, st, n, h, w);
     const unsigned blocks = (unsigned)a.strips * (unsigned)n;
     int rc;
     if (wide) {
@@ -1097,7 +1097,7 @@ int launch_flow_level(const float* R, int64_t R_stride, SlotMap map0, SlotMap ma
         for (int i = cnt; i < FDN_WS_MAX_ITERS; i++) { wa.fin[i] = nullptr; wa.fout[i] = nullptr; }
         wa.iters = cnt;
         wa.tag = next_packet_tags(cnt);
-        ProfScope ps(K_FLOW_ITER, 56.0 * cnt * n * h * w, st);
+        ProfScope ps(K_FLOW_ITER, 56.0 * cnt * n * h * w, st, n, h, w);
         const unsigned blocks = (unsigned)cnt * (unsigned)n * (unsigned)wa.strips;
         k_flow_iter_ws<2, FDN_WS_NT><<<blocks, FDN_WS_NT + 128, WsCfg2::smem_bytes, st>>>(wa);
         FDN_LAUNCHED("k_flow_iter_ws");

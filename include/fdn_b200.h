@@ -83,6 +83,10 @@ void fdn_profile_reset(void);
 int fdn_profile_kernel_count(void);
 const char* fdn_profile_kernel_name(int id);
 int fdn_profile_read(int id, double* total_ms, int64_t* launches, double* algorithmic_bytes);
+/* The individual launches behind fdn_profile_read, in launch order: kernel id, batch size and image size of the
+ * launch (0 where a launcher does not record them), device time, algorithmic bytes. Any output may be NULL. */
+int fdn_profile_record_count(void);
+int fdn_profile_record(int i, int* id, int* n, int* h, int* w, double* ms, double* algorithmic_bytes);
 
 /* ---- host-side helpers ---- */
 /* get_gaussian_kernel (src/flowdenoising.py:34-45): writes 2*int(4*sigma+0.5)+1 float64 taps, returns the
