@@ -366,21 +366,46 @@ int fdn_profile_record(int i, int* id, int* n, int* h, int* w, double* ms, doubl
     return FDN_OK;
 }
 
+// NumPy's pairwise summation (numpy/_core/src/umath/loops_utils.h.src, pairwise_sum): what ndarray.sum() computes
+// for a contiguous float64 vector. SciPy normalises the taps with it, so the order of the additions is part of the
+// reference's result.
+static double numpy_pairwise_sum(const double* a, int n)
+{
+    if (n < 8) {
+        double res = 0.;
+        for (int i = 0; i < n; i++) res += a[i];
+        return res;
+    }
+    if (n <= 128) {
+        double r[8];
+        for (int j = 0; j < 8; j++) r[j] = a[j];
+        int i;
+        for (i = 8; i < n - (n % 8); i += 8)
+            for (int j = 0; j < 8; j++) r[j] += a[i + j];
+        double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+        for (; i < n; i++) res += a[i];
+        return res;
+    }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    return numpy_pairwise_sum(a, n2) + numpy_pairwise_sum(a + n2, n - n2);
+}
+
 int fdn_gaussian_kernel(double sigma, double* taps, int cap)
 {
     // scipy.ndimage._filters._gaussian_kernel1d(sigma, 0, radius=int(4*sigma+0.5)), which is what the reference's
-    // delta-response loop (src/flowdenoising.py:34-45) returns after trimming the two exact zeros
+    // delta-response loop (src/flowdenoising.py:34-45) returns after trimming the two exact zeros:
+    // phi = exp(-0.5 / sigma^2 * x^2); phi / phi.sum()
     if (!(sigma > 0)) { set_error("sigma must be > 0"); return 0; }
     const int r = (int)(4.0 * sigma + 0.5);
     const int n = 2 * r + 1;
     if (n > cap || !taps) return -n;
     const double sigma2 = sigma * sigma;
-    double s = 0.0;
     for (int j = -r; j <= r; j++) {
         const double x = (double)j;
         taps[j + r] = exp(-0.5 / sigma2 * (x * x));
     }
-    for (int j = 0; j < n; j++) s += taps[j];
+    const double s = numpy_pairwise_sum(taps, n);
     for (int j = 0; j < n; j++) taps[j] /= s;
     return n;
 }

@@ -209,17 +209,22 @@ class DeviceEngine:
         intermediate in `vol` and the final result in `filtered_vol`; `vol` itself is not modified here."""
         torch = self.torch
         self._check_vol(vol)
+        Z, Y, X = vol.shape
+        # every volume-sized buffer exists before the first pass sizes its workspace from the free memory
         a = torch.empty_like(vol)
         b = torch.empty_like(vol)
+        ot = torch.empty((Z, X, Y), dtype=torch.float32, device=vol.device) if flow is not None else torch.empty_like(vol)
         self.filter_along_axis(vol, a, 0, kernels[0], flow, chunk, exact)
         self.filter_along_axis(a, b, 1, kernels[1], flow, chunk, exact)      # b = ZY
-        Z, Y, X = vol.shape
-        scratch = None
-        if flow is not None:
-            # `a` (the Z result) is dead now: reuse it as the transposed input of the X pass
-            scratch = (a.view(Z, X, Y), torch.empty((Z, X, Y), dtype=torch.float32, device=vol.device))
-        out = torch.empty_like(vol)
-        self.filter_along_axis(b, out, 2, kernels[2], flow, chunk, exact, scratch=scratch)
+        if flow is None:
+            self.filter_along_axis(b, ot, 2, kernels[2], flow, chunk, exact)
+            return b, ot
+        # X pass on the [Z, X, Y] transpose: `a` (the Z result) is dead now and holds first the transposed input,
+        # then -- once the pass has written `ot` -- the final result
+        vt = self.transpose_yx(b, a.view(Z, X, Y))
+        v = View(X, X, 0, 1, Z, Y, Y, X * Y, Y, X * Y)
+        self.filter_view(vt, ot, v, kernels[2], flow, chunk, exact)
+        out = self.transpose_yx(ot, a.view(Z, Y, X))
         return b, out
 
     # ---- building blocks exposed for the module-level functions and the parity tests ----

@@ -42,6 +42,13 @@ def _get_engine():
     return _ENGINE
 
 
+def release_device_memory():
+    '''Frees the pass workspace the module-level engine keeps between calls (not part of the reference's surface).'''
+    if _ENGINE is not None:
+        _ENGINE.release_workspace()
+        _ENGINE.torch.cuda.empty_cache()
+
+
 def get_gaussian_kernel(sigma=1):
     '''src/flowdenoising.py:34-45 -- same taps (SciPy's truncated Gaussian, radius int(4*sigma+0.5)).'''
     logging.info(f"Computing gaussian kernel with sigma={sigma}")
