@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfdn_b200.so")
-SOURCES = ["api.cu", "pyramid.cu", "flow.cu", "warp.cu"]
+SOURCES = ["api.cu", "pyramid.cu", "flow.cu", "warp.cu", "noof.cu"]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-lineinfo",

@@ -301,295 +301,6 @@ int launch_acc_finish(const float* centre, int64_t c_ss, int64_t c_rs, SlotMap c
 }
 
 // ------------------------------------------------------------------------------------------------
-// K5: no-OF pass, out[s] = fold_i f32(f64(acc) + f64(in[(s+halo+i-r) wrap]) * k[i])
-// ------------------------------------------------------------------------------------------------
-#define FDN_MAX_KLEN 257
-struct Taps64 {
-    int klen;
-    double k[FDN_MAX_KLEN];
-};
-struct Taps32 {
-    int klen;
-    float k[FDN_MAX_KLEN];
-};
-
-// Filter along the slice axis of a view. One thread per (y, x) column position and output slice; neighbouring
-// slices are re-read through L2 (the 2r+1 slices of a tile stay resident there).
-template <bool EXACT>
-__global__ void __launch_bounds__(256)
-k_gauss_axis(const float* __restrict__ in, float* __restrict__ out, fdn_view v, Taps64 t64, Taps32 t32)
-{
-    const int x = blockIdx.x * 256 + threadIdx.x;
-    const int y = blockIdx.y;
-    const int s = blockIdx.z;
-    if (x >= v.W) return;
-    const int klen = EXACT ? t64.klen : t32.klen;
-    const int r = klen >> 1;
-    const int64_t off = (int64_t)y * v.in_row_stride + x;
-    float acc = 0.f;
-    for (int i = 0; i < klen; i++) {
-        int j = s + v.halo + i - r;
-        if (v.periodic) {
-            j %= v.n_in;
-            if (j < 0) j += v.n_in;
-        }
-        const float val = in[(int64_t)j * v.in_slice_stride + off];
-        if (EXACT) acc = (float)__dadd_rn((double)acc, __dmul_rn((double)val, t64.k[i]));
-        else acc = fmaf(val, t32.k[i], acc);
-    }
-    out[(int64_t)s * v.out_slice_stride + (int64_t)y * v.out_row_stride + x] = acc;
-}
-
-// Sliding-window variant for the common kernel lengths: a thread owns one (y, x) column position and marches along
-// the slice axis over a segment of GA_SEG output slices, keeping the last KLEN input values in registers (the loop
-// is unrolled KLEN times so that the rotating window has static indices). Every input value is loaded once per
-// segment (+ KLEN - 1 to fill the window) instead of KLEN times: HBM-bound in float32-FMA mode; the exact mode is
-// bound by the float64 emulation of NumPy's per-tap rounding (4 dependent conversions/ops per tap).
-#define GA_SEG 128
-template <int KLEN>
-struct TapsW {
-    double k64[KLEN];
-    float k32[KLEN];
-};
-
-template <int KLEN, bool EXACT, int VEC>
-__global__ void __launch_bounds__(128)
-k_gauss_axis_win(const float* __restrict__ in, float* __restrict__ out, fdn_view v, TapsW<KLEN> taps)
-{
-    constexpr int R = KLEN / 2;
-    const int x = (blockIdx.x * 128 + threadIdx.x) * VEC;   // VEC consecutive x per thread (wide, DRAM-friendly loads)
-    const int y = blockIdx.y;
-    const int s0 = blockIdx.z * GA_SEG;
-    if (x >= v.W) return;
-    const int s_end = min(s0 + GA_SEG, v.n_out);
-    const float* src = in + (int64_t)y * v.in_row_stride + x;
-    float* dst = out + (int64_t)y * v.out_row_stride + x;
-    struct Vec { float e[VEC]; };
-    auto load = [&](int j) -> Vec {  // input slice index relative to the view, periodic wrap or explicit halo
-        j += v.halo;
-        if (v.periodic) {
-            j %= v.n_in;
-            if (j < 0) j += v.n_in;
-        }
-        const float* p = src + (int64_t)j * v.in_slice_stride;
-        Vec r;
-        if (VEC == 4) {
-            const float4 q = __ldg(reinterpret_cast<const float4*>(p));
-            r.e[0] = q.x; r.e[1 % VEC] = q.y; r.e[2 % VEC] = q.z; r.e[3 % VEC] = q.w;
-        } else {
-#pragma unroll
-            for (int c = 0; c < VEC; c++) r.e[c] = __ldg(p + c);
-        }
-        return r;
-    };
-    Vec win[KLEN];
-#pragma unroll
-    for (int i = 0; i < KLEN; i++) win[i] = load(s0 + i - R);
-    for (int s = s0; s < s_end; s += KLEN) {
-#pragma unroll
-        for (int u = 0; u < KLEN; u++) {
-            if (s + u < s_end) {
-                float acc[VEC];
-#pragma unroll
-                for (int c = 0; c < VEC; c++) acc[c] = 0.f;
-#pragma unroll
-                for (int i = 0; i < KLEN; i++) {
-#pragma unroll
-                    for (int c = 0; c < VEC; c++) {
-                        const float val = win[(u + i) % KLEN].e[c];
-                        if (EXACT) acc[c] = (float)__dadd_rn((double)acc[c], __dmul_rn((double)val, taps.k64[i]));
-                        else acc[c] = fmaf(val, taps.k32[i], acc[c]);
-                    }
-                }
-                float* d = dst + (int64_t)(s + u) * v.out_slice_stride;
-                if (VEC == 4) {
-                    *reinterpret_cast<float4*>(d) = make_float4(acc[0], acc[1 % VEC], acc[2 % VEC], acc[3 % VEC]);
-                } else {
-#pragma unroll
-                    for (int c = 0; c < VEC; c++) d[c] = acc[c];
-                }
-                if (s + u + 1 < s_end) win[u] = load(s + u + 1 + R);  // oldest value out, next slice in
-            }
-        }
-    }
-}
-
-template <int KLEN>
-static int launch_gauss_axis_win(const float* in, float* out, const fdn_view& v, const double* k, int exact,
-                                 cudaStream_t st)
-{
-    TapsW<KLEN> taps;
-    for (int i = 0; i < KLEN; i++) { taps.k64[i] = k[i]; taps.k32[i] = (float)k[i]; }
-    // 4 columns per thread when everything is 16-byte aligned and the register window stays small
-    const bool vec4 = KLEN <= 17 && v.W % 4 == 0 && v.in_row_stride % 4 == 0 && v.in_slice_stride % 4 == 0 &&
-                      v.out_row_stride % 4 == 0 && v.out_slice_stride % 4 == 0 &&
-                      (reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
-    const int vec = vec4 ? 4 : 1;
-    dim3 grid((unsigned)cdiv(v.W, 128 * vec), (unsigned)v.H, (unsigned)cdiv(v.n_out, GA_SEG));
-    ProfScope ps(K_GAUSS_AXIS, 8.0 * v.n_out * v.H * v.W, st);
-    if (vec4) {
-        if (exact) k_gauss_axis_win<KLEN, true, 4><<<grid, 128, 0, st>>>(in, out, v, taps);
-        else k_gauss_axis_win<KLEN, false, 4><<<grid, 128, 0, st>>>(in, out, v, taps);
-    } else {
-        if (exact) k_gauss_axis_win<KLEN, true, 1><<<grid, 128, 0, st>>>(in, out, v, taps);
-        else k_gauss_axis_win<KLEN, false, 1><<<grid, 128, 0, st>>>(in, out, v, taps);
-    }
-    FDN_LAUNCHED("k_gauss_axis_win");
-    return FDN_OK;
-}
-
-int launch_gauss_axis(const float* in, float* out, const fdn_view& v, const double* k, int klen, int exact,
-                      cudaStream_t st)
-{
-    FDN_CHECK_ARG(klen >= 1 && klen <= FDN_MAX_KLEN && (klen & 1), "kernel length %d unsupported (odd, <= %d)", klen,
-                  FDN_MAX_KLEN);
-    FDN_CHECK_ARG(v.H <= 65535 && v.n_out <= 65535, "view too large for one launch");
-    switch (klen) {  // sigma = 0.5, 1, 1.5, 2, 2.5, 3, 4 (radius int(4 sigma + 0.5))
-        case 5: return launch_gauss_axis_win<5>(in, out, v, k, exact, st);
-        case 9: return launch_gauss_axis_win<9>(in, out, v, k, exact, st);
-        case 13: return launch_gauss_axis_win<13>(in, out, v, k, exact, st);
-        case 17: return launch_gauss_axis_win<17>(in, out, v, k, exact, st);
-        case 21: return launch_gauss_axis_win<21>(in, out, v, k, exact, st);
-        case 25: return launch_gauss_axis_win<25>(in, out, v, k, exact, st);
-        case 33: return launch_gauss_axis_win<33>(in, out, v, k, exact, st);
-        default: break;
-    }
-    Taps64 t64;
-    Taps32 t32;
-    t64.klen = t32.klen = klen;
-    for (int i = 0; i < klen; i++) { t64.k[i] = k[i]; t32.k[i] = (float)k[i]; }
-    dim3 grid((unsigned)cdiv(v.W, 256), (unsigned)v.H, (unsigned)v.n_out);
-    ProfScope ps(K_GAUSS_AXIS, 8.0 * v.n_out * v.H * v.W, st);
-    if (exact) k_gauss_axis<true><<<grid, 256, 0, st>>>(in, out, v, t64, t32);
-    else k_gauss_axis<false><<<grid, 256, 0, st>>>(in, out, v, t64, t32);
-    FDN_LAUNCHED("k_gauss_axis");
-    return FDN_OK;
-}
-
-// Filter along contiguous rows (x axis, periodic). Row segment + wrap halo staged in shared memory.
-#define GR_TILE 512
-template <bool EXACT>
-__global__ void __launch_bounds__(256)
-k_gauss_rows(const float* __restrict__ in, float* __restrict__ out, int W, Taps64 t64, Taps32 t32)
-{
-    extern __shared__ float s_seg[];  // GR_TILE + klen - 1
-    const int klen = EXACT ? t64.klen : t32.klen;
-    const int r = klen >> 1;
-    const int64_t row = blockIdx.y;
-    const int x0 = blockIdx.x * GR_TILE;
-    const float* src = in + row * W;
-    const int nload = min(GR_TILE, W - x0) + 2 * r;
-    for (int i = threadIdx.x; i < nload; i += 256) {
-        int j = (x0 - r + i) % W;
-        if (j < 0) j += W;
-        s_seg[i] = src[j];
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < GR_TILE && x0 + i < W; i += 256) {
-        float acc = 0.f;
-        for (int t = 0; t < klen; t++) {
-            const float val = s_seg[i + t];
-            if (EXACT) acc = (float)__dadd_rn((double)acc, __dmul_rn((double)val, t64.k[t]));
-            else acc = fmaf(val, t32.k[t], acc);
-        }
-        out[row * W + x0 + i] = acc;
-    }
-}
-
-// Common kernel lengths: 4 consecutive outputs per thread from a register window filled with 128-bit shared-memory
-// loads (1.25-2.25 LDS.128 per output instead of KLEN LDS.32). W must be a multiple of 4.
-template <int KLEN, bool EXACT>
-__global__ void __launch_bounds__(128)
-k_gauss_rows4(const float* __restrict__ in, float* __restrict__ out, int W, TapsW<KLEN> taps)
-{
-    constexpr int R = KLEN / 2;
-    constexpr int PAD = (R + 3) / 4 * 4;            // halo rounded up so that the window starts 16-byte aligned
-    constexpr int NV = (4 + PAD + R + 3) / 4;       // float4 loads covering [4t - PAD + (PAD - R), 4t + 3 + R]
-    __shared__ __align__(16) float s_seg[GR_TILE + 2 * PAD];
-    const int64_t row = blockIdx.y;
-    const int x0 = blockIdx.x * GR_TILE;
-    const float* src = in + row * W;
-    const int nload = min(GR_TILE, W - x0) + 2 * PAD;
-    for (int i = threadIdx.x; i < nload; i += 128) {
-        int j = (x0 - PAD + i) % W;
-        if (j < 0) j += W;
-        s_seg[i] = src[j];
-    }
-    __syncthreads();
-    const int xo = 4 * threadIdx.x;  // outputs x0 + xo .. x0 + xo + 3
-    if (x0 + xo >= W) return;
-    float win[4 * NV];
-#pragma unroll
-    for (int v = 0; v < NV; v++) {
-        const float4 q = *reinterpret_cast<const float4*>(s_seg + xo + 4 * v);
-        win[4 * v] = q.x; win[4 * v + 1] = q.y; win[4 * v + 2] = q.z; win[4 * v + 3] = q.w;
-    }
-    float o[4];
-#pragma unroll
-    for (int e = 0; e < 4; e++) {
-        float acc = 0.f;
-#pragma unroll
-        for (int i = 0; i < KLEN; i++) {
-            const float val = win[e + (PAD - R) + i];  // input x0 + xo + e - R + i
-            if (EXACT) acc = (float)__dadd_rn((double)acc, __dmul_rn((double)val, taps.k64[i]));
-            else acc = fmaf(val, taps.k32[i], acc);
-        }
-        o[e] = acc;
-    }
-    *reinterpret_cast<float4*>(out + row * W + x0 + xo) = make_float4(o[0], o[1], o[2], o[3]);
-}
-
-template <int KLEN>
-static int launch_gauss_rows4(const float* in, float* out, int64_t rows, int W, const double* k, int exact,
-                              cudaStream_t st)
-{
-    TapsW<KLEN> taps;
-    for (int i = 0; i < KLEN; i++) { taps.k64[i] = k[i]; taps.k32[i] = (float)k[i]; }
-    for (int64_t r0 = 0; r0 < rows; r0 += 65535) {
-        const int64_t nr = rows - r0 < 65535 ? rows - r0 : 65535;
-        dim3 grid((unsigned)cdiv(W, GR_TILE), (unsigned)nr);
-        ProfScope ps(K_GAUSS_ROWS, 8.0 * nr * W, st);
-        if (exact) k_gauss_rows4<KLEN, true><<<grid, 128, 0, st>>>(in + r0 * W, out + r0 * W, W, taps);
-        else k_gauss_rows4<KLEN, false><<<grid, 128, 0, st>>>(in + r0 * W, out + r0 * W, W, taps);
-        FDN_LAUNCHED("k_gauss_rows4");
-    }
-    return FDN_OK;
-}
-
-int launch_gauss_rows(const float* in, float* out, int64_t rows, int W, const double* k, int klen, int exact,
-                      cudaStream_t st)
-{
-    FDN_CHECK_ARG(klen >= 1 && klen <= FDN_MAX_KLEN && (klen & 1), "kernel length %d unsupported (odd, <= %d)", klen,
-                  FDN_MAX_KLEN);
-    if (W % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
-        switch (klen) {
-            case 5: return launch_gauss_rows4<5>(in, out, rows, W, k, exact, st);
-            case 9: return launch_gauss_rows4<9>(in, out, rows, W, k, exact, st);
-            case 13: return launch_gauss_rows4<13>(in, out, rows, W, k, exact, st);
-            case 17: return launch_gauss_rows4<17>(in, out, rows, W, k, exact, st);
-            case 21: return launch_gauss_rows4<21>(in, out, rows, W, k, exact, st);
-            case 25: return launch_gauss_rows4<25>(in, out, rows, W, k, exact, st);
-            case 33: return launch_gauss_rows4<33>(in, out, rows, W, k, exact, st);
-            default: break;
-        }
-    }
-    Taps64 t64;
-    Taps32 t32;
-    t64.klen = t32.klen = klen;
-    for (int i = 0; i < klen; i++) { t64.k[i] = k[i]; t32.k[i] = (float)k[i]; }
-    const size_t smem = sizeof(float) * (GR_TILE + klen - 1);
-    for (int64_t r0 = 0; r0 < rows; r0 += 65535) {
-        const int64_t nr = rows - r0 < 65535 ? rows - r0 : 65535;
-        dim3 grid((unsigned)cdiv(W, GR_TILE), (unsigned)nr);
-        ProfScope ps(K_GAUSS_ROWS, 8.0 * nr * W, st);
-        if (exact) k_gauss_rows<true><<<grid, 256, smem, st>>>(in + r0 * W, out + r0 * W, W, t64, t32);
-        else k_gauss_rows<false><<<grid, 256, smem, st>>>(in + r0 * W, out + r0 * W, W, t64, t32);
-        FDN_LAUNCHED("k_gauss_rows");
-    }
-    return FDN_OK;
-}
-
-// ------------------------------------------------------------------------------------------------
 // Batched transpose of the last two axes with arbitrary outer/row strides (32x32 shared-memory tiles):
 //   out[n*out_sn + b*out_sb + a] = in[n*in_sn + a*in_sa + b],  a < A, b < B
 // Dense case ([n][A][B] -> [n][B][A]): in_sn = out_sn = A*B, in_sa = B, out_sb = A. The strided form is the

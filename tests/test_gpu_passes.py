@@ -77,6 +77,57 @@ def test_noof_large_random(eng):
         assert np.array_equal(out.cpu().numpy(), O.gauss_axis_c(vol, axis, k)), axis
 
 
+def numpy_axis_filter(vol, axis, k):
+    """The reference's arithmetic (src/flowdenoising.py:133-158 under NumPy >= 2): float64 product and sum, rounded to
+    float32 after every tap; periodic along the axis."""
+    acc = np.zeros(vol.shape, np.float32)
+    r = k.size // 2
+    with np.errstate(all="ignore"):
+        for i in range(k.size):
+            acc = (acc.astype(np.float64) + np.roll(vol, r - i, axis=axis).astype(np.float64) * k[i]).astype(np.float32)
+    return acc
+
+
+def same_bits_or_nan(a, b):
+    nan = np.isnan(a) & np.isnan(b)
+    return bool(np.all(nan | (a.view(np.uint32) == b.view(np.uint32))))
+
+
+@pytest.mark.parametrize("shape", [(40, 24, 136), (19, 8, 512), (140, 6, 20)])
+def test_noof_exact_special_values(eng, shape):
+    """The exact mode rounds most taps with integer instructions, which is valid for zero / normal float32 sums only;
+    anything else (subnormals, huge values, infinities, NaN, tiny values that cancel) must fall back to conversions.
+    Covers aligned and unaligned widths (vector widths 1 / 2 / 4) and segments longer than one window period."""
+    rng = np.random.default_rng(3)
+    vol = (rng.standard_normal(shape) * 50).astype(np.float32)
+    flat = vol.reshape(-1)
+    n = flat.size
+    pick = lambda m: rng.choice(n, m, replace=False)
+    flat[pick(n // 7)] = 0.0
+    flat[pick(n // 50)] = -0.0
+    flat[pick(n // 40)] = np.float32(1e-42)          # subnormal
+    flat[pick(n // 40)] = np.float32(-3e-39)
+    flat[pick(n // 40)] = np.float32(2.5e-12)        # normal, below the integer path's range
+    flat[pick(n // 40)] = np.float32(3e33)           # above it
+    flat[pick(n // 60)] = np.float32(3e38)           # sums overflow to +-inf
+    flat[pick(n // 60)] = np.float32(-3e38)
+    flat[pick(n // 200)] = np.inf
+    flat[pick(n // 200)] = np.nan
+    for axis, sigma in [(0, 2.0), (1, 0.5), (2, 2.0), (0, 4.0), (2, 1.0)]:
+        k = O.get_gaussian_kernel(sigma)
+        out = torch.empty_like(dev(vol))
+        eng.filter_along_axis(dev(vol), out, axis, k, None)
+        assert same_bits_or_nan(out.cpu().numpy(), numpy_axis_filter(vol, axis, k)), (axis, sigma)
+    # cancellation: values of similar magnitude and opposite sign, tiny and ordinary
+    vol2 = (rng.standard_normal(shape) * 1e-8).astype(np.float32)
+    vol2[::2] *= -1
+    for axis in range(3):
+        k = O.get_gaussian_kernel(1.5)
+        out = torch.empty_like(dev(vol2))
+        eng.filter_along_axis(dev(vol2), out, axis, k, None)
+        assert same_bits_or_nan(out.cpu().numpy(), numpy_axis_filter(vol2, axis, k)), axis
+
+
 def test_of_passes_vs_reference_toy(eng, golden):
     from flowdenoising_b200.engine import FlowParams
     g = golden("toy_of.npz")

@@ -107,3 +107,31 @@ def test_synthetic_volume_reproducible_and_cfg1_slice(golden):
     out = np.zeros_like(vol)
     O.flow_axis_c(vol, 0, k, s0=37, s1=38, out=out)
     assert np.array_equal(out[37], g["Z"][1])
+
+
+def test_veltkamp_split_is_round_to_nearest_even_float32():
+    """The exact no-OF kernels (csrc/noof.cu) round a float64 sum to float32 precision with Veltkamp's splitting
+    (p = s * (2^29 + 1); hi = (s - p) + p) instead of a double -> float -> double conversion pair. The two must agree
+    for every zero / float32-normal value, exact ties (round half to even) and mantissa carries included."""
+    rng = np.random.default_rng(1)
+    n = 3_000_000
+    expo = rng.integers(1023 - 112, 1023 + 127, n, dtype=np.uint64)
+    mant_hi = rng.integers(0, 2 ** 20, n, dtype=np.uint64)
+    top3 = rng.integers(0, 8, n, dtype=np.uint64)
+    kind = rng.integers(0, 6, n)
+    mant_hi = np.where(kind >= 4, np.uint64(0xFFFFF), mant_hi)          # all ones above the rounding position
+    top3 = np.where(kind >= 4, np.uint64(7), top3)
+    low29 = np.where(kind % 2 == 0, np.uint64(0x10000000), rng.integers(0, 2 ** 29, n, dtype=np.uint64))   # exact ties
+    low29 = np.where(kind == 3, np.uint64(0x10000000) + rng.integers(-1, 2, n).astype(np.int64).astype(np.uint64),
+                     low29) & np.uint64(0x1FFFFFFF)
+    bits = (expo << np.uint64(52)) | (mant_hi << np.uint64(32)) | (top3 << np.uint64(29)) | low29
+    s = bits.view(np.float64)
+    s = np.where(rng.integers(0, 2, n) == 1, -s, s)
+    s[:4] = [0.0, -0.0, 2.0 ** -112, -(2.0 ** 127)]
+    with np.errstate(over="ignore"):
+        ref = s.astype(np.float32).astype(np.float64)
+    ok = np.isfinite(ref)                                               # (values that round up to 2^128 overflow)
+    p = s * (2.0 ** 29 + 1)
+    hi = (s - p) + p
+    assert np.count_nonzero(low29 == 0x10000000) > 1_000_000
+    assert np.array_equal(hi[ok].view(np.uint64), ref[ok].view(np.uint64))
