@@ -36,6 +36,8 @@ SIGNATURES = {
     "fdn_last_error": (C.c_char_p, []),
     "fdn_launch_count": (c_i64, []),
     "fdn_reset_launch_count": (None, []),
+    "fdn_progress_milli": (c_i64, []),
+    "fdn_progress_reset": (None, []),
     "fdn_profile_enable": (None, [C.c_int]),
     "fdn_profile_reset": (None, []),
     "fdn_profile_kernel_count": (C.c_int, []),

@@ -11,6 +11,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
+#include <mutex>
 #include <vector>
 
 #include "fdn_internal.cuh"
@@ -18,7 +20,7 @@
 namespace fdn {
 
 static thread_local char g_err[512] = "";
-int64_t g_launches = 0;
+std::atomic<int64_t> g_launches{0};
 
 void set_error(const char* fmt, ...)
 {
@@ -38,6 +40,7 @@ struct ProfRec {
 };
 static std::vector<ProfRec> g_prof;
 static std::vector<cudaEvent_t> g_event_pool;
+static std::mutex g_prof_mutex;   // the record list is shared by every host thread that launches with profiling on
 static const char* const g_kernel_names[K_COUNT] = {
     "k_blur_rows", "k_blur_cols", "k_resize_linear_img", "k_polyexp", "k_flow_iter", "k_flow_area_down",
     "k_flow_upsample", "k_warp_acc", "k_gauss_axis", "k_gauss_rows", "k_transpose", "k_copy3d"};
@@ -54,8 +57,9 @@ static cudaEvent_t get_event()
     return e;
 }
 
-void prof_begin(int id, double bytes, cudaStream_t st, int n, int h, int w)
+int prof_begin(int id, double bytes, cudaStream_t st, int n, int h, int w)
 {
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
     ProfRec r;
     r.a = get_event();
     r.b = get_event();
@@ -64,11 +68,26 @@ void prof_begin(int id, double bytes, cudaStream_t st, int n, int h, int w)
     r.n = n; r.h = h; r.w = w;
     cudaEventRecord(r.a, st);
     g_prof.push_back(r);
+    return (int)g_prof.size() - 1;
 }
 
-void prof_end(cudaStream_t st) { cudaEventRecord(g_prof.back().b, st); }
+void prof_end(int rec, cudaStream_t st)
+{
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
+    if (rec >= 0 && rec < (int)g_prof.size()) cudaEventRecord(g_prof[rec].b, st);
+}
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---- progress feedback (src/flowdenoising.py:139-140, :292-295: the reference counts finished slices) ----
+// Thousandths of a slice, advanced by host functions placed in the stream after every chain step: the count follows
+// what the device has EXECUTED, not what the host has enqueued.
+static std::atomic<long long> g_progress_milli{0};
+static void CUDART_CB progress_cb(void* data) { g_progress_milli.fetch_add((long long)(intptr_t)data); }
+static void progress_add(cudaStream_t st, long long milli)
+{
+    if (milli > 0) cudaLaunchHostFunc(st, progress_cb, (void*)(intptr_t)milli);
+}
 
 struct Geometry {
     int nl;  // extra levels
@@ -298,11 +317,13 @@ static int filter_axis_of(const float* d_in, float* d_out, const fdn_view& v, co
                                        v.out_slice_stride, v.out_row_stride, stash + (size_t)(d - 1) * C * H * W, C, H, W,
                                        d == 1 ? 1 : 0, st)))
                 return rc;
+            progress_add(st, 1000ll * C / (r + 1));
         }
         SlotMap cmap{c0 + v.halo, wrap_in};
         if ((rc = launch_acc_finish(d_in, v.in_slice_stride, v.in_row_stride, cmap, stash, r, kernel + r, acc,
                                     v.out_slice_stride, v.out_row_stride, C, H, W, r > 0 ? 1 : 0, st)))
             return rc;
+        progress_add(st, 1000ll * C - (long long)r * (1000ll * C / (r + 1)));
     }
     return FDN_OK;
 }
@@ -316,13 +337,16 @@ extern "C" {
 
 int fdn_version(void) { return 100; }
 const char* fdn_last_error(void) { return g_err; }
-int64_t fdn_launch_count(void) { return g_launches; }
-void fdn_reset_launch_count(void) { g_launches = 0; }
+int64_t fdn_launch_count(void) { return g_launches.load(); }
+int64_t fdn_progress_milli(void) { return (int64_t)g_progress_milli.load(); }
+void fdn_progress_reset(void) { g_progress_milli.store(0); }
+void fdn_reset_launch_count(void) { g_launches.store(0); }
 
 void fdn_profile_enable(int on) { g_prof_on = on != 0; }
 
 void fdn_profile_reset(void)
 {
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
     for (auto& r : g_prof) { g_event_pool.push_back(r.a); g_event_pool.push_back(r.b); }
     g_prof.clear();
 }
@@ -333,6 +357,7 @@ const char* fdn_profile_kernel_name(int id) { return (id >= 0 && id < K_COUNT) ?
 int fdn_profile_read(int id, double* total_ms, int64_t* launches, double* algorithmic_bytes)
 {
     FDN_CHECK_ARG(id >= 0 && id < K_COUNT, "bad kernel id %d", id);
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
     double ms = 0, bytes = 0;
     int64_t n = 0;
     for (auto& r : g_prof) {
@@ -348,10 +373,15 @@ int fdn_profile_read(int id, double* total_ms, int64_t* launches, double* algori
     return FDN_OK;
 }
 
-int fdn_profile_record_count(void) { return (int)g_prof.size(); }
+int fdn_profile_record_count(void)
+{
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
+    return (int)g_prof.size();
+}
 
 int fdn_profile_record(int i, int* id, int* n, int* h, int* w, double* ms, double* algorithmic_bytes)
 {
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
     FDN_CHECK_ARG(i >= 0 && i < (int)g_prof.size(), "bad record index %d", i);
     ProfRec& r = g_prof[i];
     FDN_CUDA(cudaEventSynchronize(r.b));
@@ -459,7 +489,9 @@ int fdn_gauss_axis(const float* d_in, float* d_out, const fdn_view* view, const 
     FDN_CHECK_ARG(klen >= 1 && (klen & 1), "kernel length must be odd");
     if (v.periodic) FDN_CHECK_ARG(v.halo == 0 && v.n_in == v.n_out, "periodic views must have halo == 0");
     else FDN_CHECK_ARG(v.halo >= klen / 2 && v.n_in >= v.n_out + v.halo + klen / 2, "halo too small");
-    return launch_gauss_axis(d_in, d_out, v, kernel, klen, exact, static_cast<cudaStream_t>(stream));
+    int rc = launch_gauss_axis(d_in, d_out, v, kernel, klen, exact, static_cast<cudaStream_t>(stream));
+    if (rc == FDN_OK) progress_add(static_cast<cudaStream_t>(stream), 1000ll * v.n_out);
+    return rc;
 }
 
 int fdn_gauss_rows(const float* d_in, float* d_out, int64_t n_rows, int W, const double* kernel, int klen, int exact,

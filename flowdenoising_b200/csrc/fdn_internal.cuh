@@ -2,6 +2,8 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+
+#include <atomic>
 #include <stdio.h>
 
 #include "fdn_b200.h"
@@ -10,7 +12,7 @@ namespace fdn {
 
 // ---- error plumbing (no exceptions across the C ABI) ----
 void set_error(const char* fmt, ...);
-extern int64_t g_launches;
+extern std::atomic<int64_t> g_launches;   // (engines on several host threads may launch concurrently)
 
 #define FDN_CHECK_ARG(cond, ...)                 \
     do {                                         \
@@ -50,16 +52,16 @@ enum KernelId {
     K_GAUSS_AXIS, K_GAUSS_ROWS, K_TRANSPOSE, K_COPY3D, K_COUNT
 };
 extern bool g_prof_on;
-void prof_begin(int id, double algorithmic_bytes, cudaStream_t st, int n = 0, int h = 0, int w = 0);
-void prof_end(cudaStream_t st);
+int prof_begin(int id, double algorithmic_bytes, cudaStream_t st, int n = 0, int h = 0, int w = 0);   // -> record index
+void prof_end(int record, cudaStream_t st);
 struct ProfScope {
     cudaStream_t st;
-    bool on;
-    ProfScope(int id, double bytes, cudaStream_t s, int n = 0, int h = 0, int w = 0) : st(s), on(g_prof_on)
+    int rec;
+    ProfScope(int id, double bytes, cudaStream_t s, int n = 0, int h = 0, int w = 0) : st(s), rec(-1)
     {
-        if (on) prof_begin(id, bytes, s, n, h, w);
+        if (g_prof_on) rec = prof_begin(id, bytes, s, n, h, w);
     }
-    ~ProfScope() { if (on) prof_end(st); }
+    ~ProfScope() { if (rec >= 0) prof_end(rec, st); }
 };
 
 // ---- constants passed by value to kernels ----

@@ -176,8 +176,9 @@ k_blur_cols(const float* __restrict__ in, float* __restrict__ out, int H, int W,
     out[((int64_t)b * H + y) * W + x] = acc;
 }
 
-// Register-window variants for the tap counts the Farneback pyramid actually uses (3, 7, 17 taps: half widths 1, 3,
-// 8). Same arithmetic per output as k_blur_rows / k_blur_cols; each thread produces 4 outputs from one window of
+// Register-window variants for the tap counts the Farneback pyramid actually uses: ksz = max(rint(5 sigma_k) | 1, 3)
+// with sigma_k = (2^k - 1) / 2 -> 3, 3, 9, 19, 39, 79 taps for levels 0..5 (half widths 1, 4, 9, 19, 39; SURVEY.md
+// App. A.0). Same arithmetic per output as k_blur_rows / k_blur_cols; each thread produces 4 outputs from one window of
 // 4 + 2R inputs instead of 4 * (2R + 1) loads with their address arithmetic.
 template <int R>
 __global__ void __launch_bounds__(128)
@@ -253,8 +254,8 @@ k_blur_cols4(const float* __restrict__ in, float* __restrict__ out, int H, int W
 int launch_blur_rows(const float* in, int64_t in_ss, int64_t in_rs, SlotMap in_map, float* out, int n, int H,
                      int W, const BlurTaps& bt, cudaStream_t st)
 {
-    const bool win4 = (bt.ksz == 3 || bt.ksz == 7 || bt.ksz == 17) && W % 4 == 0 && W >= 4 + bt.ksz &&
-                      (reinterpret_cast<uintptr_t>(out) & 15) == 0 && H <= 65535;
+    const bool win4 = (bt.ksz == 3 || bt.ksz == 9 || bt.ksz == 19 || bt.ksz == 39 || bt.ksz == 79) && W % 4 == 0 &&
+                      W >= 4 + bt.ksz && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && H <= 65535;
     for (int b0 = 0; b0 < n; b0 += 65535) {
         int nb = n - b0 < 65535 ? n - b0 : 65535;
         SlotMap m = in_map;
@@ -264,8 +265,10 @@ int launch_blur_rows(const float* in, int64_t in_ss, int64_t in_rs, SlotMap in_m
             dim3 grid((unsigned)cdiv(W, 512), (unsigned)H, (unsigned)nb);
             float* o = out + (int64_t)b0 * H * W;
             if (bt.ksz == 3) k_blur_rows4<1><<<grid, 128, 0, st>>>(in, in_ss, in_rs, m, o, H, W, bt);
-            else if (bt.ksz == 7) k_blur_rows4<3><<<grid, 128, 0, st>>>(in, in_ss, in_rs, m, o, H, W, bt);
-            else k_blur_rows4<8><<<grid, 128, 0, st>>>(in, in_ss, in_rs, m, o, H, W, bt);
+            else if (bt.ksz == 9) k_blur_rows4<4><<<grid, 128, 0, st>>>(in, in_ss, in_rs, m, o, H, W, bt);
+            else if (bt.ksz == 19) k_blur_rows4<9><<<grid, 128, 0, st>>>(in, in_ss, in_rs, m, o, H, W, bt);
+            else if (bt.ksz == 39) k_blur_rows4<19><<<grid, 128, 0, st>>>(in, in_ss, in_rs, m, o, H, W, bt);
+            else k_blur_rows4<39><<<grid, 128, 0, st>>>(in, in_ss, in_rs, m, o, H, W, bt);
             FDN_LAUNCHED("k_blur_rows4");
             continue;
         }
@@ -278,7 +281,7 @@ int launch_blur_rows(const float* in, int64_t in_ss, int64_t in_rs, SlotMap in_m
 
 int launch_blur_cols(const float* in, float* out, int n, int H, int W, const BlurTaps& bt, cudaStream_t st)
 {
-    const bool win4 = (bt.ksz == 3 || bt.ksz == 7 || bt.ksz == 17) && H >= 4 + bt.ksz;
+    const bool win4 = (bt.ksz == 3 || bt.ksz == 9 || bt.ksz == 19 || bt.ksz == 39 || bt.ksz == 79) && H >= 4 + bt.ksz;
     for (int b0 = 0; b0 < n; b0 += 65535) {
         int nb = n - b0 < 65535 ? n - b0 : 65535;
         ProfScope ps(K_BLUR_COLS, 8.0 * nb * H * W, st);
@@ -287,8 +290,10 @@ int launch_blur_cols(const float* in, float* out, int n, int H, int W, const Blu
         if (win4) {
             dim3 grid((unsigned)cdiv(W, 128), (unsigned)cdiv(H, 4), (unsigned)nb);
             if (bt.ksz == 3) k_blur_cols4<1><<<grid, 128, 0, st>>>(i_, o_, H, W, bt);
-            else if (bt.ksz == 7) k_blur_cols4<3><<<grid, 128, 0, st>>>(i_, o_, H, W, bt);
-            else k_blur_cols4<8><<<grid, 128, 0, st>>>(i_, o_, H, W, bt);
+            else if (bt.ksz == 9) k_blur_cols4<4><<<grid, 128, 0, st>>>(i_, o_, H, W, bt);
+            else if (bt.ksz == 19) k_blur_cols4<9><<<grid, 128, 0, st>>>(i_, o_, H, W, bt);
+            else if (bt.ksz == 39) k_blur_cols4<19><<<grid, 128, 0, st>>>(i_, o_, H, W, bt);
+            else k_blur_cols4<39><<<grid, 128, 0, st>>>(i_, o_, H, W, bt);
             FDN_LAUNCHED("k_blur_cols4");
             continue;
         }
@@ -442,6 +447,9 @@ __device__ __forceinline__ void tma_load_box(uint64_t tmap_addr, uint32_t dst, u
         :: "r"(dst), "l"(tmap_addr), "r"(cx), "r"(cy), "r"(cz), "r"(bar) : "memory");
 }
 
+// NC > 0: poly_n known at compile time (5, the reference's constant): tile pitches, the divisions by them and the tap
+// loops fold; NC == 0: generic.
+template <int NC>
 __global__ void __launch_bounds__(256)
 k_polyexp_tma(const __grid_constant__ CUtensorMap tmap, float* __restrict__ R, int64_t R_stride, SlotMap R_map, int h,
               int w, PolyConsts pc)
@@ -449,7 +457,7 @@ k_polyexp_tma(const __grid_constant__ CUtensorMap tmap, float* __restrict__ R, i
     __shared__ __align__(128) float s_in[2][PBY_MAX * PBX_MAX];
     __shared__ float s_row[3][PT][PT + 2 * PN_MAX + 1];
     __shared__ __align__(8) unsigned long long s_bar[2];
-    const int n = pc.n;
+    const int n = NC > 0 ? NC : pc.n;
     const int TW = PT + 2 * n;           // columns / rows actually used
     const int BX = (PL + PT + n + 3) & ~3;   // box width (multiple of 4 floats = 16 bytes), the tile's row pitch
     const int y0 = blockIdx.y * PT, b = blockIdx.z;
@@ -486,7 +494,9 @@ k_polyexp_tma(const __grid_constant__ CUtensorMap tmap, float* __restrict__ R, i
             if (!border) {
                 const float* c = tin + (ty + n) * BX + tx + (PL - n);
                 t0 = __fmul_rn(c[0], pc.g[0]);
-                for (int k = 1; k <= n; k++) {
+#pragma unroll
+    #pragma unroll
+            for (int k = 1; k <= n; k++) {
                     const float a0 = c[-k * BX], a1 = c[k * BX];
                     const float p = __fadd_rn(a0, a1);
                     t0 = __fadd_rn(t0, __fmul_rn(pc.g[k], p));
@@ -498,7 +508,9 @@ k_polyexp_tma(const __grid_constant__ CUtensorMap tmap, float* __restrict__ R, i
                 const int gy = gy0 + ty + n;
                 const float* col = tin + cx;
                 t0 = __fmul_rn(col[(min(max(gy, 0), h - 1) - gy0) * BX], pc.g[0]);
-                for (int k = 1; k <= n; k++) {
+#pragma unroll
+    #pragma unroll
+            for (int k = 1; k <= n; k++) {
                     const float a0 = col[(min(max(gy - k, 0), h - 1) - gy0) * BX];
                     const float a1 = col[(min(max(gy + k, 0), h - 1) - gy0) * BX];
                     const float p = __fadd_rn(a0, a1);
@@ -521,6 +533,7 @@ k_polyexp_tma(const __grid_constant__ CUtensorMap tmap, float* __restrict__ R, i
             float g0 = pc.g[0];
             double b1 = (double)__fmul_rn(r0[0], g0), b2 = 0, b3 = (double)__fmul_rn(r1[0], g0), b4 = 0,
                    b5 = (double)__fmul_rn(r2[0], g0), b6 = 0;
+#pragma unroll
             for (int k = 1; k <= n; k++) {
                 const double tg = (double)__fadd_rn(r0[k], r0[-k]);
                 g0 = pc.g[k];
@@ -593,7 +606,8 @@ int launch_polyexp(const float* img, int64_t img_stride, float* R, int64_t R_str
         if (cr == CUDA_SUCCESS) {
             dim3 grid(1, (unsigned)cdiv(h, PT), (unsigned)n);
             ProfScope ps(K_POLYEXP, 24.0 * n * h * w, st);
-            k_polyexp_tma<<<grid, 256, 0, st>>>(tmap, R, R_stride, R_map, h, w, pc);
+            if (pc.n == 5) k_polyexp_tma<5><<<grid, 256, 0, st>>>(tmap, R, R_stride, R_map, h, w, pc);
+            else k_polyexp_tma<0><<<grid, 256, 0, st>>>(tmap, R, R_stride, R_map, h, w, pc);
             FDN_LAUNCHED("k_polyexp_tma");
             return FDN_OK;
         }

@@ -59,6 +59,113 @@ def _to_dev(a, torch, dev):
     return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev, non_blocking=False)
 
 
+_STAGE_BYTES = 64 << 20
+_PINNED = {}
+
+
+def _pinned_pair(torch):
+    """Two pinned staging buffers per process (page-locking is expensive: they are kept)."""
+    if "bufs" not in _PINNED:
+        _PINNED["bufs"] = [torch.empty(_STAGE_BYTES // 4, dtype=torch.float32, pin_memory=True) for _ in range(2)]
+    return _PINNED["bufs"]
+
+
+def _is_pinned_f32(a, torch):
+    if not (isinstance(a, np.ndarray) and a.dtype == np.float32 and a.flags.c_contiguous and a.flags.writeable):
+        return False
+    try:
+        return bool(torch.from_numpy(a).is_pinned())
+    except Exception:
+        return False
+
+
+def _upload_volume(vol, torch, dev):
+    """Host volume (any dtype / layout NumPy can cast to float32, pageable or pinned) -> float32 device tensor.
+    A pinned float32 array is copied directly; anything else goes through two pinned staging buffers, the host-side
+    cast/copy of chunk k+1 overlapping the DMA of chunk k (a pageable cudaMemcpy would serialise the two)."""
+    shape = tuple(int(s) for s in vol.shape)
+    d = torch.empty(shape, dtype=torch.float32, device=dev)
+    if _is_pinned_f32(vol, torch):
+        d.copy_(torch.from_numpy(vol), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return d
+    bufs = _pinned_pair(torch)
+    plane = int(np.prod(shape[1:]))
+    step = max(1, (_STAGE_BYTES // 4) // plane)
+    if plane > _STAGE_BYTES // 4:      # a single plane larger than the staging buffer: plain copy
+        d.copy_(torch.from_numpy(np.ascontiguousarray(vol, dtype=np.float32)))
+        return d
+    evs = [None, None]
+    for i, z0 in enumerate(range(0, shape[0], step)):
+        z1 = min(shape[0], z0 + step)
+        b = bufs[i & 1][:(z1 - z0) * plane].view((z1 - z0,) + shape[1:])
+        if evs[i & 1] is not None:
+            evs[i & 1].synchronize()
+        np.copyto(b.numpy(), vol[z0:z1], casting="unsafe")
+        d[z0:z1].copy_(b, non_blocking=True)
+        evs[i & 1] = torch.cuda.Event()
+        evs[i & 1].record()
+    torch.cuda.current_stream().synchronize()
+    return d
+
+
+class _Download:
+    """Device tensor -> caller's array on a side stream (and, for pageable / non-float32 destinations, a host thread
+    that drains pinned staging chunks), so that the copy overlaps whatever the main stream does next."""
+
+    def __init__(self, t, dst, torch):
+        self.torch = torch
+        self.t = t
+        self.dst = dst
+        self.stream = torch.cuda.Stream(device=t.device)
+        self.ready = torch.cuda.Event()
+        self.ready.record()                      # on the current stream: `t` is complete after this point
+        self.thread = None
+        if _is_pinned_f32(dst, torch):
+            with torch.cuda.stream(self.stream):
+                self.stream.wait_event(self.ready)
+                torch.from_numpy(dst).copy_(t, non_blocking=True)
+        else:
+            self.thread = threading.Thread(target=self._drain, daemon=True)
+            self.thread.start()
+
+    def _drain(self):
+        torch = self.torch
+        t, dst = self.t, self.dst
+        shape = tuple(t.shape)
+        plane = int(np.prod(shape[1:]))
+        if plane > _STAGE_BYTES // 4:
+            self.ready.synchronize()
+            dst[...] = t.cpu().numpy()
+            return
+        step = max(1, (_STAGE_BYTES // 4) // plane)
+        bufs = [torch.empty(_STAGE_BYTES // 4, dtype=torch.float32, pin_memory=True) for _ in range(2)]
+        with torch.cuda.device(t.device), torch.cuda.stream(self.stream):
+            self.stream.wait_event(self.ready)
+            chunks = [(z0, min(shape[0], z0 + step)) for z0 in range(0, shape[0], step)]
+            evs = []
+            def issue(i):
+                z0, z1 = chunks[i]
+                b = bufs[i & 1][:(z1 - z0) * plane].view((z1 - z0,) + shape[1:])
+                b.copy_(t[z0:z1], non_blocking=True)
+                e = torch.cuda.Event(); e.record(self.stream)
+                evs.append((e, b))
+            if chunks:
+                issue(0)
+            for i, (z0, z1) in enumerate(chunks):
+                e, b = evs[i]
+                e.synchronize()
+                if i + 1 < len(chunks):
+                    # the other buffer is free: its previous contents were copied out in the previous iteration
+                    issue(i + 1)
+                np.copyto(dst[z0:z1], b.numpy(), casting="unsafe")
+
+    def wait(self):
+        if self.thread is not None:
+            self.thread.join()
+        self.stream.synchronize()
+
+
 def _to_host(t, dst, torch):
     '''Device tensor -> caller's ndarray; straight into its memory when it is a writable float32 C array (a pinned
     array then gets a pinned-speed copy), through a cast otherwise (integer volumes, quirk Q3).'''
@@ -119,7 +226,8 @@ class GaussianDenoising():
     '''src/flowdenoising.py:116-295.'''
 
     def __init__(self, number_of_processes, vol):
-        self.progress = 0.0
+        self._progress_done = 0.0
+        self._progress_mark = None      # library counter at the start of the device call in flight
         self.number_of_processes = number_of_processes
         self.vol = vol
         vol_size = vol.dtype.itemsize * vol.size
@@ -131,21 +239,77 @@ class GaussianDenoising():
         self.filtered_vol = np.zeros_like(vol)
         self._flow_params = None  # no OF
         self.exact = True         # no-OF arithmetic: bit-exact NumPy emulation (False: float32 FMA)
+        # beyond the reference's surface (set after construction; the CLI maps --border / --gpus / --slab_slices):
+        self.border = "wrap"      # "mean": the sequential variant's padding (src/flowdenoising_sequential.py:88-89)
+        self.devices = None       # CUDA devices to spread slabs over (None: the current one)
+        self.slab_slices = None   # output slices per streamed slab (None: sized from the free device memory)
+        self.streaming = None     # None: stream slab by slab only when needed (memory map, > device memory, ...)
+
+    # The reference bumps `progress` once per finished slice (:139-140) and feedback() prints it (:292-295). Here the
+    # count of the device call in flight comes from the library (host functions in the stream after every chain step).
+    @property
+    def progress(self):
+        live = 0.0
+        if self._progress_mark is not None:
+            live = _engine._lib.load().fdn_progress_milli() / 1000.0 - self._progress_mark
+        return self._progress_done + live
+
+    @progress.setter
+    def progress(self, value):
+        self._progress_done = float(value)
+
+    def _begin_device_call(self):
+        self._progress_mark = _engine._lib.load().fdn_progress_milli() / 1000.0
+
+    def _end_device_call(self, slices_done):
+        self._progress_mark = None
+        self._progress_done += slices_done
 
     # -- device plumbing --
     def _flow(self):
         return self._flow_params
+
+    def _streaming_needed(self):
+        if self.streaming is not None:
+            return bool(self.streaming)
+        if isinstance(self.vol, np.memmap) or self.border != "wrap" or (self.devices and len(self.devices) > 1):
+            return True
+        eng = _get_engine()
+        free, _total = eng.torch.cuda.mem_get_info(eng.device)
+        # in core: the volume, two intermediates and the result as float32, plus a workspace worth having
+        return 4 * 4 * self.vol.size + (2 << 30) > 0.9 * free
+
+    def _streamer(self):
+        from .streaming import StreamingDenoiser
+        done0 = [self._progress_done]
+
+        def report(slices):
+            self._progress_done = done0[0] + slices
+        sd = StreamingDenoiser(self._flow(), exact=self.exact, border=self.border, slab_slices=self.slab_slices,
+                               devices=self.devices, progress=report)
+        return sd, done0
 
     def _pass(self, axis, kernel):
         eng = _get_engine()
         torch = eng.torch
         kernel = np.asarray(kernel, dtype=np.float64)
         assert kernel.size % 2 != 0  # kernel.size must be odd (src/flowdenoising.py:309)
-        d_in = _to_dev(self.vol, torch, eng.device)
+        if self._streaming_needed():
+            sd, done0 = self._streamer()
+            dst = self.filtered_vol if self.filtered_vol.dtype == np.float32 else np.empty(self.vol.shape, np.float32)
+            sd.filter_axis(self.vol, dst, axis, kernel)
+            if dst is not self.filtered_vol:
+                self.filtered_vol[...] = dst
+            sd.release()
+            self._progress_done = done0[0] + self.vol.shape[axis]
+            return
+        d_in = _upload_volume(self.vol, torch, eng.device)
         d_out = torch.empty_like(d_in)
+        self._begin_device_call()
         eng.filter_along_axis(d_in, d_out, axis, kernel, self._flow(), exact=self.exact)
-        _to_host(d_out, self.filtered_vol, torch)
-        self.progress += self.vol.shape[axis]
+        dl = _Download(d_out, self.filtered_vol, torch)
+        dl.wait()
+        self._end_device_call(self.vol.shape[axis])
 
     def filter_along_Z(self, kernel):
         logging.info(f"Filtering along Z with kernel length={kernel.size}")
@@ -205,16 +369,62 @@ class GaussianDenoising():
 
     def filter(self, kernels):
         '''src/flowdenoising.py:285-290: Z, Y, X passes; vol ends as the Z+Y intermediate, filtered_vol as the
-        Z+Y+X result. One upload, three device passes, two downloads.'''
+        Z+Y+X result. In core: one upload (pinned staging), three device passes, the download of the Z+Y
+        intermediate overlapping the X pass. Volumes that are memory-mapped, larger than the device, spread over
+        several devices or mean-padded stream through the device(s) slab by slab (streaming.py).'''
         eng = _get_engine()
         torch = eng.torch
         for k in kernels:
             assert np.asarray(k).size % 2 != 0
-        d_in = _to_dev(self.vol, torch, eng.device)
-        zy, zyx = eng.filter(d_in, [np.asarray(k, np.float64) for k in kernels], self._flow(), exact=self.exact)
-        _to_host(zy, self.vol, torch)
-        _to_host(zyx, self.filtered_vol, torch)
-        self.progress = float(np.sum(self.vol.shape))
+        ks = [np.asarray(k, np.float64) for k in kernels]
+        Z, Y, X = (int(v) for v in self.vol.shape)
+        if self._streaming_needed():
+            sd, done0 = self._streamer()
+            fv = self.filtered_vol if self.filtered_vol.dtype == np.float32 else np.empty(self.vol.shape, np.float32)
+            base = done0[0]
+            zy, zyx = None, None
+            # three passes with the reference's buffer roles: vol -> scratch -> vol (Z+Y) -> filtered_vol
+            writable = isinstance(self.vol, np.ndarray) and self.vol.dtype == np.float32 and self.vol.flags.writeable
+            scratch = np.empty(self.vol.shape, np.float32)
+            mean = float(np.float32(np.mean(self.vol))) if self.border == "mean" else None
+            sd.filter_axis(self.vol, scratch, 0, ks[0], mean)
+            done0[0] = base + Z
+            zy = self.vol if writable else np.empty(self.vol.shape, np.float32)
+            sd.filter_axis(scratch, zy, 1, ks[1], mean)
+            done0[0] = base + Z + Y
+            del scratch
+            sd.filter_axis(zy, fv, 2, ks[2], mean)
+            sd.release()
+            if not writable:
+                try:
+                    self.vol[...] = zy      # integer volumes: truncation, like the reference (Q3); read-only maps: skip
+                except (ValueError, TypeError):
+                    pass
+            if fv is not self.filtered_vol:
+                self.filtered_vol[...] = fv
+            self._progress_done = base + Z + Y + X
+            return self.filtered_vol
+        flow = self._flow()
+        d_in = _upload_volume(self.vol, torch, eng.device)
+        a = torch.empty_like(d_in)
+        b = torch.empty_like(d_in)
+        ot = torch.empty((Z, X, Y), dtype=torch.float32, device=d_in.device) if flow is not None else torch.empty_like(d_in)
+        self._begin_device_call()
+        eng.filter_along_axis(d_in, a, 0, ks[0], flow, exact=self.exact)
+        eng.filter_along_axis(a, b, 1, ks[1], flow, exact=self.exact)          # b = Z+Y
+        dl_zy = _Download(b, self.vol, torch)                                   # ... goes home while X runs
+        if flow is None:
+            eng.filter_along_axis(b, ot, 2, ks[2], None, exact=self.exact)
+            out = ot
+        else:
+            vt = eng.transpose_yx(b, a.view(Z, X, Y))
+            v = _engine.View(X, X, 0, 1, Z, Y, Y, X * Y, Y, X * Y)
+            eng.filter_view(vt, ot, v, ks[2], flow, exact=self.exact)
+            out = eng.transpose_yx(ot, a.view(Z, Y, X))
+        dl = _Download(out, self.filtered_vol, torch)
+        dl.wait()
+        dl_zy.wait()
+        self._end_device_call(Z + Y + X)
         return self.filtered_vol
 
     def feedback(self):
@@ -270,8 +480,17 @@ def build_parser():
     parser.add_argument("-m", "--memory_map", action="store_true",
                         help="Enable memory-mapping (only for MRC files)")
     parser.add_argument("-p", "--number_of_processes", type=int_or_str,
-                        help="Maximum number of processes (accepted for compatibility; slices are batched on the GPU)",
+                        help="Maximum number of processes (accepted for compatibility; slices are batched on the GPU, "
+                             "see --gpus)",
                         default=number_of_PUs)
+    parser.add_argument("--gpus", type=int, default=1,
+                        help="Number of GPUs of this node to spread each pass over (slabs of slices with an r-slice halo)")
+    parser.add_argument("--border", choices=["wrap", "mean"], default="wrap",
+                        help="Border along the filtered axis: periodic like flowdenoising.py, or padded with the "
+                             "volume's mean like flowdenoising_sequential.py")
+    parser.add_argument("--slab_slices", type=int, default=None,
+                        help="Output slices per streamed slab when the volume does not stay on the device "
+                             "(default: sized from the free device memory)")
     parser.add_argument("--recompute_flow", action="store_true", help="Disable the use of adjacent optical flow fields")
     parser.add_argument("--show_fingerprint", action="store_true", help="Show a hash of this file")
     parser.add_argument("--iterations", type=int, default=OF_ITERS, help="Farneback iterations per pyramid level")
@@ -330,7 +549,9 @@ def main(argv=None):
     time_0 = time.perf_counter()
     vol = volume_io.read_volume(args.input, memory_map=args.memory_map)
     logging.info(f"read \"{args.input}\" in {time.perf_counter() - time_0} seconds")
-    vol = np.ascontiguousarray(vol, dtype=np.float32)
+    mapped = isinstance(vol, np.memmap)
+    if not mapped:      # (-m: the volume stays in the file and streams through the device slab by slab)
+        vol = np.ascontiguousarray(vol, dtype=np.float32)
 
     kernels = [get_gaussian_kernel(s) for s in sigma]
     logging.info(f"length of each filter (Z, Y, X) = {[len(i) for i in kernels]}")
@@ -344,6 +565,18 @@ def main(argv=None):
     else:
         fd = FlowDenoising(args.number_of_processes, vol, args.levels, args.winsize, get_flow, warp_slice,
                            iterations=args.iterations, poly_n=args.poly_n, poly_sigma=args.poly_sigma)
+    fd.border = args.border
+    fd.slab_slices = args.slab_slices
+    if args.gpus > 1:
+        import torch
+        if args.gpus > torch.cuda.device_count():
+            parser.error(f"--gpus {args.gpus}: this node has {torch.cuda.device_count()} CUDA devices")
+        fd.devices = list(range(args.gpus))
+    out_map = None
+    if mapped and volume_io.is_mrc_output(args.output) and not args.compat_zy_output:
+        # the result is written in place into the output file as well
+        out_map = volume_io.create_mrc_memmap(args.output, vol.shape)
+        fd.filtered_vol = out_map
 
     thread = threading.Thread(target=fd.feedback)
     thread.daemon = True  # To obey CTRL+C interruption.
@@ -354,7 +587,7 @@ def main(argv=None):
     time_0 = time.perf_counter()
     filtered_vol = fd.filter(kernels)
     if args.compat_zy_output:
-        filtered_vol = vol.copy()
+        filtered_vol = np.array(fd.vol, dtype=np.float32)
     logging.info(f"Volume filtered in {time.perf_counter() - time_0} seconds")
 
     logging.info(f"{args.output} type = {filtered_vol.dtype}")
@@ -364,7 +597,10 @@ def main(argv=None):
 
     logging.info(f"writing \"{args.output}\"")
     time_0 = time.perf_counter()
-    volume_io.write_volume(args.output, filtered_vol.astype(np.float32))
+    if out_map is not None:
+        volume_io.finish_mrc_memmap(args.output, out_map)
+    else:
+        volume_io.write_volume(args.output, np.asarray(filtered_vol, dtype=np.float32))
     logging.info(f"written \"{args.output}\" in {time.perf_counter() - time_0} seconds")
     return 0
 

@@ -67,11 +67,7 @@ def read_mrc(path: str, memory_map: bool = False) -> np.ndarray:
     return data
 
 
-def write_mrc(path: str, vol: np.ndarray):
-    vol = np.ascontiguousarray(vol, dtype="<f4")
-    if vol.ndim != 3:
-        raise ValueError("MRC output needs a 3-D volume")
-    nz, ny, nx = vol.shape
+def _mrc_header(nz, ny, nx, dmin, dmax, dmean, rms):
     h = bytearray(1024)
     struct.pack_into("<4i", h, 0, nx, ny, nz, 2)
     struct.pack_into("<3i", h, 16, 0, 0, 0)
@@ -79,10 +75,6 @@ def write_mrc(path: str, vol: np.ndarray):
     struct.pack_into("<3f", h, 40, float(nx), float(ny), float(nz))   # 1 A voxels
     struct.pack_into("<3f", h, 52, 90.0, 90.0, 90.0)
     struct.pack_into("<3i", h, 64, 1, 2, 3)
-    v64 = vol.astype(np.float64) if vol.size < (1 << 28) else None
-    dmin, dmax = float(vol.min()), float(vol.max())
-    dmean = float(vol.mean(dtype=np.float64))
-    rms = float(v64.std()) if v64 is not None else float(np.sqrt(max(0.0, np.mean(np.square(vol, dtype=np.float64)) - dmean ** 2)))
     struct.pack_into("<3f", h, 76, dmin, dmax, dmean)
     struct.pack_into("<2i", h, 88, 1, 0)           # ispg = 1 (volume), nsymbt = 0
     h[104:108] = b"\0\0\0\0"                       # exttyp
@@ -93,9 +85,49 @@ def write_mrc(path: str, vol: np.ndarray):
     label = ("Created by flowdenoising_b200 " + time.strftime("%Y-%m-%d %H:%M:%S")).encode()[:80]
     struct.pack_into("<i", h, 220, 1)
     h[224:224 + len(label)] = label
+    return h
+
+
+def _stats(vol):
+    """min, max, mean, rms deviation, plane by plane (works on memory maps without materialising the volume)."""
+    dmin, dmax, s1, s2 = np.inf, -np.inf, 0.0, 0.0
+    for z in range(vol.shape[0]):
+        p = np.asarray(vol[z], dtype=np.float64)
+        dmin = min(dmin, float(p.min())); dmax = max(dmax, float(p.max()))
+        s1 += float(p.sum()); s2 += float(np.square(p).sum())
+    n = float(vol.size)
+    mean = s1 / n
+    return dmin, dmax, mean, float(np.sqrt(max(0.0, s2 / n - mean * mean)))
+
+
+def write_mrc(path: str, vol: np.ndarray):
+    vol = np.ascontiguousarray(vol, dtype="<f4")
+    if vol.ndim != 3:
+        raise ValueError("MRC output needs a 3-D volume")
+    nz, ny, nx = vol.shape
+    h = _mrc_header(nz, ny, nx, *_stats(vol))
     with open(path, "wb") as f:
         f.write(h)
         vol.tofile(f)
+
+
+def create_mrc_memmap(path: str, shape) -> np.memmap:
+    """A mode-2 (float32) MRC file of the given (nz, ny, nx) shape whose data block is returned as a writable memory
+    map: out-of-core results are written in place (`-m`). Call finish_mrc_memmap() when the data is complete."""
+    nz, ny, nx = (int(v) for v in shape)
+    with open(path, "wb") as f:
+        f.write(_mrc_header(nz, ny, nx, 0.0, 0.0, 0.0, 0.0))
+        f.truncate(1024 + 4 * nz * ny * nx)
+    return np.memmap(path, dtype="<f4", mode="r+", offset=1024, shape=(nz, ny, nx))
+
+
+def finish_mrc_memmap(path: str, mm: np.memmap):
+    """Flushes the map and fills in the header's density statistics."""
+    mm.flush()
+    nz, ny, nx = mm.shape
+    h = _mrc_header(nz, ny, nx, *_stats(mm))
+    with open(path, "r+b") as f:
+        f.write(h)
 
 
 # ---------------------------------------------------------------- TIFF

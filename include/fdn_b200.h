@@ -73,6 +73,12 @@ const char* fdn_last_error(void);
 /* Number of this library's kernel launches since the last reset (bench.py "gpu_launches"). */
 int64_t fdn_launch_count(void);
 void fdn_reset_launch_count(void);
+/* Progress feedback for the reference's feedback() thread (src/flowdenoising.py:139-140, :292-295): thousandths of
+ * output slices the device has finished since the last reset, all passes of this process together. A pass advances it
+ * after every chain step (host functions in the stream), so it follows execution, not enqueueing. fdn_gauss_rows
+ * (slices are not its unit) does not touch it. */
+int64_t fdn_progress_milli(void);
+void fdn_progress_reset(void);
 
 /* Optional per-kernel timing: when enabled every kernel launch is bracketed by CUDA events on the launching
  * stream. fdn_profile_read(id) synchronises on them and returns, for kernel `id` (0 <= id <

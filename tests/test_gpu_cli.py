@@ -38,3 +38,52 @@ def test_cli_mrc_and_tiff_roundtrip(tmp_path, golden):
     assert fd.main(["-i", str(src), "-o", str(out4), "-s", sig[0], "0.1", "0.1", "--recompute_flow",
                     "--compat_zy_output"]) == 0   # sigma 0.1 -> r = int(0.9) = 0: single-tap kernels, the Y pass is the identity
     assert np.array_equal(volume_io.read_volume(str(out4)), r["Z"])
+
+
+def test_cli_memory_map_streams_slabs(tmp_path, golden):
+    """-m: the input stays a memory map and streams through the device in slabs (here 5 slices), the result is written
+    in place into the output MRC; same bits as the in-core run."""
+    from flowdenoising_b200 import flowdenoising as fd
+    from flowdenoising_b200 import volume_io
+    g = golden("toy_of.npz")
+    vol = g["vol"].astype(np.float32)
+    sig = [str(float(s)) for s in g["sigmas"]]
+    src = tmp_path / "toy.mrc"
+    volume_io.write_mrc(str(src), vol)
+    out = tmp_path / "out.mrc"
+    assert fd.main(["-i", str(src), "-o", str(out), "-s", *sig, "-m", "--slab_slices", "5"]) == 0
+    assert np.array_equal(volume_io.read_volume(str(out)), g["ZYX"])
+    assert np.array_equal(volume_io.read_volume(str(src)), vol)               # the input file is not rewritten (Q4)
+    # two "GPUs" worth of lanes need two devices: on a one-GPU box the flag must be refused, not ignored
+    if torch.cuda.device_count() < 2:
+        with pytest.raises(SystemExit):
+            fd.main(["-i", str(src), "-o", str(out), "-s", *sig, "--gpus", "2"])
+    else:
+        out2 = tmp_path / "out2.mrc"
+        assert fd.main(["-i", str(src), "-o", str(out2), "-s", *sig, "--gpus", "2", "--slab_slices", "4"]) == 0
+        assert np.array_equal(volume_io.read_volume(str(out2)), g["ZYX"])
+
+
+def test_progress_follows_the_device(golden):
+    """feedback() reads `progress` (src/flowdenoising.py:292-295); it must advance with the passes and end at Z+Y+X."""
+    import threading
+    import time
+    from flowdenoising_b200 import flowdenoising as fd
+    from oracle import fd_oracle as O
+    vol = O.synthetic_volume((24, 96, 128), seed=9, noise_sigma=6.0)
+    obj = fd.FlowDenoising(1, vol.copy(), 3, 5, fd.get_flow_with_prev_flow, fd.warp_slice)
+    seen = []
+    stop = threading.Event()
+
+    def poll():
+        while not stop.is_set():
+            seen.append(obj.progress)
+            time.sleep(0.002)
+    th = threading.Thread(target=poll)
+    th.start()
+    obj.filter([fd.get_gaussian_kernel(1.0)] * 3)
+    stop.set(); th.join()
+    total = float(sum(vol.shape))
+    assert obj.progress == total
+    assert all(b >= a for a, b in zip(seen, seen[1:])) and max(seen) <= total
+    assert len({round(v, 3) for v in seen if 0 < v < total}) >= 1       # intermediate values were observable
