@@ -502,7 +502,23 @@ def main():
         e2e_s = float(np.mean(times))
         e2e = {"value": nvox / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(nvox * 4),
                "d2h_bytes_per_step": int(nvox * 8), "ms_per_step": e2e_s * 1e3, "steps": n_e2e,
-               "api": "flowdenoising_b200.flowdenoising.FlowDenoising(P, vol_numpy, ...).filter(kernels)"}
+               "api": "flowdenoising_b200.flowdenoising.FlowDenoising(P, vol_numpy, ...).filter(kernels)",
+               "host_memory": "pinned (torch pin_memory arrays handed to the classes)"}
+        # the same call from ordinary (pageable) NumPy arrays, as a CLI user has them: one sample
+        try:
+            pv = np.array(pristine.numpy())
+            obj = fd.GaussianDenoising(os.cpu_count(), pv) if args.no_of else \
+                fd.FlowDenoising(os.cpu_count(), pv, args.levels, args.winsize, fd.get_flow_with_prev_flow, fd.warp_slice)
+            obj.exact = exact
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            obj.filter(kernels)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            e2e["pageable"] = {"value": nvox / dt / 1e6, "ms_per_step": dt * 1e3, "steps": 1}
+            del pv
+        except MemoryError:
+            pass
         del host, pristine, obj
         fd.release_device_memory()
     elif world > 1 and not args.skip_e2e:
