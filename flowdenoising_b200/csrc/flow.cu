@@ -409,8 +409,16 @@ struct RowIn {
 template <int MT, int NT_>
 struct WsCfg {
     static constexpr int NT = NT_;
-    static constexpr int TR = 2 * MT + 2;   // tile rows = ring period
-    static constexpr int SR = MT + 1;       // rows per straight-line block
+    static constexpr int RR = 2 * MT + 2;   // ring period: rows of M a column keeps
+    // tile rows: one ring period when its 5 * RR lines fit the lanes of the one scan warp (winsize 5: 6 rows), else half
+    // a period (winsize 9: 5 rows, the two tiles of a period are the two shared-memory tiles)
+    static constexpr int TR = 5 * RR <= 32 ? RR : RR / 2;
+    static constexpr int TPP = RR / TR;     // tiles per ring period
+#ifndef FDN_WS_SR4
+#define FDN_WS_SR4 2
+#endif
+    static constexpr int SR = MT == 4 ? FDN_WS_SR4 : 3;   // rows per straight-line block of phase V
+    static constexpr int NB = (TR + SR - 1) / SR;
     static constexpr int HALO = 2 * MT + 1;
     static constexpr int CWMAX = (NT - HALO) & ~3;
     static constexpr int NCH = (CWMAX + 31) / 32;   // 32-column chunks of a strip (scan -> solve hand-off)
@@ -418,6 +426,8 @@ struct WsCfg {
     static constexpr size_t tiles_bytes = 2 * sizeof(double) * TR * 5 * LS + 128;   // two tiles (+ the scan's read-ahead past the last line)
     static constexpr size_t smem_bytes = tiles_bytes + 8 * 2 * NCH + 16;      // + the chunk mbarriers, the ticket
     static_assert(5 * TR <= 32, "phase H runs in one warp");
+    static_assert(TR * TPP == RR && (TPP == 1 || TPP == 2), "a ring period is one tile or the two shared-memory tiles");
+    static_assert(HALO + 8 <= 17, "the scan's register window spans two 8-column sets and one more column");
 };
 
 // The eight bilinear taps of one pixel (R1 at the displaced position), read at clamped -- always valid -- positions.
@@ -494,6 +504,21 @@ __device__ __forceinline__ void ws_matrices_px(const RowIn& in, const Taps& tp, 
     M[4] = __fadd_rn(__fmul_rn(r6, r2), __fmul_rn(r5, r3));
 }
 
+// Phase H keeps a register window of 17 tile positions: two 8-column sets (four 128-bit loads each) and the first pair
+// of the set after them. `idx` is a compile-time constant after unrolling.
+__device__ __forceinline__ double ws_win(const double2 (&W0)[4], const double2 (&W1)[4], const double2& X, int idx)
+{
+    return idx < 8 ? ((idx & 1) ? W0[idx >> 1].y : W0[idx >> 1].x)
+                   : idx < 16 ? ((idx & 1) ? W1[(idx - 8) >> 1].y : W1[(idx - 8) >> 1].x) : X.x;
+}
+// D[u] = pos[8k + u + OFF] - pos[8k + u] for the 8 columns of chunk k (W0 = set k, W1 = set k+1, X = first pair of set k+2)
+template <int OFF>
+__device__ __forceinline__ void ws_diffs(double (&D)[8], const double2 (&W0)[4], const double2 (&W1)[4], const double2& X)
+{
+#pragma unroll
+    for (int u = 0; u < 8; u++) D[u] = __dsub_rn(ws_win(W0, W1, X, u + OFF), ws_win(W0, W1, X, u));
+}
+
 // phase-removal experiments exist only in -DFDN_WS_EXPERIMENTS builds: in product builds the tests fold to constants
 // (no branches inside the straight-line blocks of phase V)
 #ifdef FDN_WS_EXPERIMENTS
@@ -555,7 +580,7 @@ __global__ void __launch_bounds__(NT_ + 128, 2)
 k_flow_iter_ws(WsArgs wa)
 {
     using C = WsCfg<MT, NT_>;
-    constexpr int NT = C::NT, TR = C::TR, SR = C::SR, RR = C::TR, LS = C::LS, NCH = C::NCH, m = MT;
+    constexpr int NT = C::NT, TR = C::TR, SR = C::SR, RR = C::RR, TPP = C::TPP, NB = C::NB, LS = C::LS, NCH = C::NCH, m = MT;
     constexpr int BAR_FULL = 1, BAR_FREE = 5, BAR_SOLVED = 7;
     constexpr unsigned WARPS = (NT + 128) / 32;
     extern __shared__ __align__(128) unsigned char smem_ws[];
@@ -666,7 +691,7 @@ k_flow_iter_ws(WsArgs wa)
         ulonglong2* pk_out = wa.packets + ((int64_t)b * wa.strips + k) * h * 5;
         const ulonglong2* pk_in = wa.packets + ((int64_t)b * wa.strips + max(k - 1, 0)) * h * 5;
         constexpr int off = 2 * m + 1;
-        static_assert(off == 5 && FDN_WS_HC == 8, "the sliding window below is written for m = 2, 8-column chunks");
+        static_assert(FDN_WS_HC == 8, "the sliding window below is written for 8-column chunks");
         for (int j = 0; j < ntiles; j++) {
             const int y = j * TR + r;
             const uint32_t bars = smem_u32(chunk_bar + (j & 1) * NCH);
@@ -676,19 +701,13 @@ k_flow_iter_ws(WsArgs wa)
                 double* line = tiles + ((j & 1) * TR * 5 + r * 5 + c) * LS;
                 double2* l2 = reinterpret_cast<double2*>(line);   // 16-byte aligned (LS is even)
                 // S(i) = S(i-1) + (vs[i+m] - vs[i-m-1]); S(i) overwrites the dead slot of column i-m-1.
-                // The line is read ONCE, 128 bits at a time, through a sliding window of two 8-column sets: while the
-                // chain of chunk k runs (8 dependent DADDs, then four 128-bit stores) the set after next is in flight
-                // and the differences of chunk k+1 are formed from the two sets in registers.
-                // positions 8k .. 8k+7 = set k; d_k[u] = pos[8k + u + 5] - pos[8k + u] needs sets k and k+1
+                // The line is read ONCE, 128 bits at a time, through a sliding window of two 8-column sets (plus, for
+                // winsize 9, the first pair of the third): while the chain of chunk k runs (8 dependent DADDs, then four
+                // 128-bit stores) the set after next is in flight and the differences of chunk k+1 are formed from the
+                // sets in registers. positions 8k .. 8k+7 = set k; d_k[u] = pos[8k + u + off] - pos[8k + u].
 #define FDN_LOADSET(W, kk)                                                        \
-    { W[0] = l2[4 * (kk)]; W[1] = l2[4 * (kk) + 1]; W[2] = l2[4 * (kk) + 2]; W[3] = l2[4 * (kk) + 3]; }
-#define FDN_DIFFS(D, W0, W1)                                                       \
-    {                                                                              \
-        D[0] = __dsub_rn(W0[2].y, W0[0].x); D[1] = __dsub_rn(W0[3].x, W0[0].y);    \
-        D[2] = __dsub_rn(W0[3].y, W0[1].x); D[3] = __dsub_rn(W1[0].x, W0[1].y);    \
-        D[4] = __dsub_rn(W1[0].y, W0[2].x); D[5] = __dsub_rn(W1[1].x, W0[2].y);    \
-        D[6] = __dsub_rn(W1[1].y, W0[3].x); D[7] = __dsub_rn(W1[2].x, W0[3].y);    \
-    }
+    { W[0] = l2[4 * (kk)]; W[1] = l2[4 * (kk) + 1]; W[2] = l2[4 * (kk) + 2]; W[3] = l2[4 * (kk) + 3];   \
+      if (off > 7) xx_ = l2[4 * (kk) + 4]; }
 #define FDN_CHAIN8(D, kk)                                                          \
     {                                                                              \
         double2 s0, s1, s2, s3;                                                    \
@@ -705,7 +724,7 @@ k_flow_iter_ws(WsArgs wa)
         if (lane == 0) mbar_arrive(bars + 8 * (((kk) >> 2) - 1));                  \
     }
                 const int n8 = ncols >> 3;   // full chunks; ncols % 8 is 0 or 4
-                double2 wa_[4], wb_[4];
+                double2 wa_[4], wb_[4], xx_ = make_double2(0., 0.);   // xx_: first pair of the set after the newest one
                 double d[8];
                 FDN_LOADSET(wa_, 0);
                 FDN_LOADSET(wb_, 1);   // (a line has LS >= ncols + 2m + 1 + 8 readable positions)
@@ -713,6 +732,7 @@ k_flow_iter_ws(WsArgs wa)
                 if (k == 0) {
                     // g = vsum[0]*(m+2) + vsum[1] + ... + vsum[m-1]   (columns clamp to the replicated border)
                     S = __dmul_rn(line[m + 1], (double)(m + 2));
+#pragma unroll
                     for (int x = 1; x < m; x++) S = __dadd_rn(S, line[m + 1 + x]);
                 } else if (FDN_WS_EXP(2)) {
                     S = 0.;
@@ -727,20 +747,20 @@ k_flow_iter_ws(WsArgs wa)
                 }
                 __syncwarp(hmask);   // the lanes leave their polling loops one by one: scan in lockstep from here on
                 if (!FDN_WS_EXP(1)) {
-                    FDN_DIFFS(d, wa_, wb_);
+                    ws_diffs<off>(d, wa_, wb_, xx_);
                     int kk = 0;
                     while (kk < n8) {
                         // sets: wa_ = kk, wb_ = kk+1; d = differences of chunk kk
                         FDN_LOADSET(wa_, kk + 2);
                         FDN_CHAIN8(d, kk);
-                        FDN_DIFFS(d, wb_, wa_);
+                        ws_diffs<off>(d, wb_, wa_, xx_);
                         ++kk;
                         FDN_CHUNK_DONE(kk);
                         if (kk == n8) break;
                         // sets: wb_ = kk, wa_ = kk+1
                         FDN_LOADSET(wb_, kk + 2);
                         FDN_CHAIN8(d, kk);
-                        FDN_DIFFS(d, wa_, wb_);
+                        ws_diffs<off>(d, wa_, wb_, xx_);
                         ++kk;
                         FDN_CHUNK_DONE(kk);
                     }
@@ -752,7 +772,6 @@ k_flow_iter_ws(WsArgs wa)
                     }
                 }
 #undef FDN_LOADSET
-#undef FDN_DIFFS
 #undef FDN_CHAIN8
 #undef FDN_CHUNK_DONE
                 if (k + 1 < wa.strips) {
@@ -841,56 +860,65 @@ k_flow_iter_ws(WsArgs wa)
         for (int r = 0; r < TR; r++) cur[r] = load_row(r + m);
     }
 
-    for (int j = 0; j < ntiles; j++) {
-        const int y0 = j * TR;
-        double* tq = tiles + (j & 1) * TR * 5 * LS + t;
-        if (j >= 2) nbar_sync(BAR_FREE + (j & 1), 96 + NT);   // tile j-2 has been solved: its shared-memory tile is free
-        // ---------------- phase V ----------------
+    // One trip of the outer loop = one ring period = TPP tiles: every ring slot below is a compile-time constant.
+    for (int jp = 0; jp < ntiles; jp += TPP) {
 #pragma unroll
-        for (int half = 0; half < 2; half++) {
-            // the SR rows of a half are independent up to the column sums: one straight-line block (all the gathers
-            // first, then the arithmetic of the rows interleaved by the compiler).
-            Taps tp[SR];
+        for (int tp = 0; tp < TPP; tp++) {
+            const int j = jp + tp;
+            if (TPP > 1 && j >= ntiles) break;
+            const int y0 = j * TR;
+            const int buf = TPP > 1 ? tp : (j & 1);   // (jp is even when a period is two tiles)
+            double* tq = tiles + buf * TR * 5 * LS + t;
+            if (j >= 2) nbar_sync(BAR_FREE + buf, 96 + NT);   // tile j-2 has been solved: its shared-memory tile is free
+            // ---------------- phase V ----------------
 #pragma unroll
-            for (int rr = 0; rr < SR; rr++) {
-                const int r = half * SR + rr;
-                tp[rr] = ws_gather<FDN_WS_PF>(cur[r].f, R1a, R1b, xcl, min(y0 + r + m, h - 1), h, w);
-            }
-            float Mv[SR][5];
-#pragma unroll
-            for (int rr = 0; rr < SR; rr++) {
-                const int r = half * SR + rr;
-                ws_matrices_px(cur[r], tp[rr], xcl, min(y0 + r + m, h - 1), h, w, sxc, Mv[rr]);
-            }
-            // The column-sum update sits behind a branch the compiler cannot fold (the packet tag is never 0): it keeps
-            // the two halves of a tile apart for the scheduler. Merged into one basic block, ptxas hoists the gathers of
-            // all 2*SR rows, the register allocation collapses and the launch is 20 % slower (measured: 10.3 instead of
-            // 8.5 ms for 512 pairs).
-            if (wa.tag != 0 && !FDN_WS_EXP(4)) {
+            for (int blk = 0; blk < NB; blk++) {
+                // the (up to) SR rows of a block are independent up to the column sums: one straight-line block (all the
+                // gathers first, then the arithmetic of the rows interleaved by the compiler).
+                Taps tps[SR];
 #pragma unroll
                 for (int rr = 0; rr < SR; rr++) {
-                    const int r = half * SR + rr;
-                    const int snew = (r + m) % RR, sold = (r + m + 1) % RR;
+                    const int r = blk * SR + rr;
+                    if (r < TR) tps[rr] = ws_gather<FDN_WS_PF>(cur[r].f, R1a, R1b, xcl, min(y0 + r + m, h - 1), h, w);
+                }
+                float Mv[SR][5];
 #pragma unroll
-                    for (int c = 0; c < 5; c++) {
-                        const float d = __fsub_rn(Mv[rr][c], Mring[sold][c]);
-                        Mring[snew][c] = Mv[rr][c];
-                        vs[c] = __dadd_rn(vs[c], (double)d);
-                        tq[(r * 5 + c) * LS] = vs[c];
+                for (int rr = 0; rr < SR; rr++) {
+                    const int r = blk * SR + rr;
+                    if (r < TR) ws_matrices_px(cur[r], tps[rr], xcl, min(y0 + r + m, h - 1), h, w, sxc, Mv[rr]);
+                }
+                // The column-sum update sits behind a branch the compiler cannot fold (the packet tag is never 0): it
+                // keeps the blocks of a tile apart for the scheduler. Merged into one basic block, ptxas hoists the
+                // gathers of all rows, the register allocation collapses and the launch is 20 % slower (measured: 10.3
+                // instead of 8.5 ms for 512 pairs).
+                if (wa.tag != 0 && !FDN_WS_EXP(4)) {
+#pragma unroll
+                    for (int rr = 0; rr < SR; rr++) {
+                        const int r = blk * SR + rr;
+                        if (r < TR) {
+                            const int snew = (tp * TR + r + m) % RR, sold = (tp * TR + r + m + 1) % RR;
+#pragma unroll
+                            for (int c = 0; c < 5; c++) {
+                                const float d = __fsub_rn(Mv[rr][c], Mring[sold][c]);
+                                Mring[snew][c] = Mv[rr][c];
+                                vs[c] = __dadd_rn(vs[c], (double)d);
+                                tq[(r * 5 + c) * LS] = vs[c];
+                            }
+                        }
                     }
                 }
-            }
-            // R0 / flow of the same rows of the NEXT tile: in flight for a whole tile period
+                // R0 / flow of the same rows of the NEXT tile: in flight for a whole tile period
 #pragma unroll
-            for (int rr = 0; rr < SR; rr++) cur[half * SR + rr] = load_row(y0 + TR + half * SR + rr + m);
-#ifdef FDN_WS_MIDFENCE
-            if (half == 0) __threadfence_block();
-#endif
-        }
+                for (int rr = 0; rr < SR; rr++) {
+                    const int r = blk * SR + rr;
+                    if (r < TR) cur[r] = load_row(y0 + TR + r + m);
+                }
+            }
 #ifndef FDN_WS_NOFENCE
-        __threadfence_block();
+            __threadfence_block();
 #endif
-        nbar_arrive(BAR_FULL + (j & 1), NT + 32);          // the scan warp may start on tile j
+            nbar_arrive(BAR_FULL + buf, NT + 32);          // the scan warp may start on tile j
+        }
     }
     warp_exit();
 }
@@ -918,7 +946,13 @@ static int ws_strip_width(int w, int cwmax)
     return (int)((cdiv(w, strips) + 3) / 4 * 4);
 }
 #define FDN_WS_NT 128
-typedef WsCfg<2, FDN_WS_NT> WsCfg2;
+typedef WsCfg<2, FDN_WS_NT> WsCfg2;   // winsize 5
+typedef WsCfg<4, FDN_WS_NT> WsCfg4;   // winsize 9
+static int ws_strips_max(int w)   // strips of the narrower configuration: what the packet area is sized for
+{
+    const int a = (int)cdiv(w, ws_strip_width(w, WsCfg2::CWMAX)), b = (int)cdiv(w, ws_strip_width(w, WsCfg4::CWMAX));
+    return a > b ? a : b;
+}
 
 static size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 
@@ -940,7 +974,7 @@ int flow_scratch_make(void* scratch, size_t bytes, int cap_n, int H, int W, Flow
     fs->off_done = off;    off += align256(sizeof(unsigned) * FDN_WS_MAX_ITERS * (size_t)cap_n);
     fs->off_flags = off;   off += align256(sizeof(unsigned long long) * (size_t)cap_n * FDN_MAX_STRIPS);
     fs->off_packets = off;
-    off += align256(sizeof(ulonglong2) * 5 * (size_t)cap_n * (size_t)cdiv(W, ws_strip_width(W, WsCfg2::CWMAX)) * H);
+    off += align256(sizeof(ulonglong2) * 5 * (size_t)cap_n * (size_t)ws_strips_max(W) * H);
     fs->off_carry = off;
     off += align256(sizeof(double) * 5 * (size_t)cap_n * (size_t)cdiv(W, strip_width(W)) * H);
     if (scratch && bytes < off) {
@@ -1029,6 +1063,28 @@ static int launch_flow_iter_strip(const float* R, int64_t R_stride, SlotMap map0
     return FDN_OK;
 }
 
+template <int MT>
+static int launch_ws(const WsArgs& wa, unsigned blocks, cudaStream_t st)
+{
+    using C = WsCfg<MT, FDN_WS_NT>;
+    static std::atomic<bool> seen[64];
+    if (first_use_on_device(seen)) {
+        FDN_CUDA(cudaFuncSetAttribute(k_flow_iter_ws<MT, FDN_WS_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)C::smem_bytes));
+        // leave the rest of the SM's L1/shared array to L1: the R1 rows a strip walks over live there
+        FDN_CUDA(cudaFuncSetAttribute(k_flow_iter_ws<MT, FDN_WS_NT>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                      (int)((2 * (C::smem_bytes + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024))));
+        if (getenv("FDN_DEBUG")) {
+            int nb = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_flow_iter_ws<MT, FDN_WS_NT>, FDN_WS_NT + 128, C::smem_bytes);
+            fprintf(stderr, "[fdn] k_flow_iter_ws<%d>: %d blocks/SM, %zu B shared memory per block\n", MT, nb,
+                    (size_t)C::smem_bytes);
+        }
+    }
+    k_flow_iter_ws<MT, FDN_WS_NT><<<blocks, FDN_WS_NT + 128, C::smem_bytes, st>>>(wa);
+    return FDN_OK;
+}
+
 int launch_flow_level(const float* R, int64_t R_stride, SlotMap map0, SlotMap map1, float* cur, float* bufa, float* bufb,
                       int n, int h, int w, int winsize, int iters, const FlowScratch& fs, cudaStream_t st,
                       float** result)
@@ -1042,7 +1098,7 @@ int launch_flow_level(const float* R, int64_t R_stride, SlotMap map0, SlotMap ma
     float* bufs[3] = {cur, bufa, bufb};
     const int m = winsize / 2;
     // warp-specialised variant (default for winsize 5 on images that are not tiny)
-    const bool win = g_flow_variant.load() == 1 && m == 2 && w % 4 == 0 && w >= 64 && h >= 16 &&
+    const bool win = g_flow_variant.load() == 1 && (m == 2 || m == 4) && w % 4 == 0 && w >= 64 && h >= 16 &&
                      (reinterpret_cast<uintptr_t>(R) & 15) == 0 && R_stride % 4 == 0;
     if (!win) {
         for (int i = 0; i < iters; i++) {
@@ -1058,27 +1114,12 @@ int launch_flow_level(const float* R, int64_t R_stride, SlotMap map0, SlotMap ma
     wa.map0 = map0; wa.map1 = map1;
     wa.n = n; wa.h = h; wa.w = w;
     wa.scale = 1. / ((double)winsize * winsize);
-    wa.CW = ws_strip_width(w, WsCfg2::CWMAX);
+    wa.CW = ws_strip_width(w, m == 2 ? WsCfg2::CWMAX : WsCfg4::CWMAX);
     wa.strips = (int)cdiv(w, wa.CW);
     FDN_CHECK_ARG(wa.strips <= FDN_MAX_STRIPS, "image too wide (%d strips)", wa.strips);
     wa.ctl = reinterpret_cast<unsigned*>(fs.base);
     wa.done = reinterpret_cast<unsigned*>(fs.base + fs.off_done);
     wa.packets = reinterpret_cast<ulonglong2*>(fs.base + fs.off_packets);
-    static std::atomic<bool> seen[64];
-    if (first_use_on_device(seen)) {
-        FDN_CUDA(cudaFuncSetAttribute(k_flow_iter_ws<2, FDN_WS_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)WsCfg2::smem_bytes));
-        // leave the rest of the SM's L1/shared array to L1: the R1 rows a strip walks over live there
-        FDN_CUDA(cudaFuncSetAttribute(k_flow_iter_ws<2, FDN_WS_NT>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                      (int)((2 * (WsCfg2::smem_bytes + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024))));
-        if (getenv("FDN_DEBUG")) {
-            int nb = 0;
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_flow_iter_ws<2, FDN_WS_NT>, FDN_WS_NT + 128,
-                                                          WsCfg2::smem_bytes);
-            fprintf(stderr, "[fdn] k_flow_iter_ws: %d blocks/SM, %zu B shared memory per block\n", nb,
-                    (size_t)WsCfg2::smem_bytes);
-        }
-    }
     wa.exp = 0;
 #ifdef FDN_WS_EXPERIMENTS   // phase-removal timing experiments of tools/flow_iter_lab.py (FDN_EXP bit mask): wrong results
     { const char* e = getenv("FDN_EXP"); wa.exp = e ? atoi(e) : 0; }
@@ -1099,7 +1140,8 @@ int launch_flow_level(const float* R, int64_t R_stride, SlotMap map0, SlotMap ma
         wa.tag = next_packet_tags(cnt);
         ProfScope ps(K_FLOW_ITER, 56.0 * cnt * n * h * w, st, n, h, w);
         const unsigned blocks = (unsigned)cnt * (unsigned)n * (unsigned)wa.strips;
-        k_flow_iter_ws<2, FDN_WS_NT><<<blocks, FDN_WS_NT + 128, WsCfg2::smem_bytes, st>>>(wa);
+        int rc = m == 2 ? launch_ws<2>(wa, blocks, st) : launch_ws<4>(wa, blocks, st);
+        if (rc) return rc;
         FDN_LAUNCHED("k_flow_iter_ws");
     }
     *result = bufs[iters % 3];

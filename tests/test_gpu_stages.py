@@ -158,10 +158,12 @@ def _run_iterations(eng, dR, n, flow, h, w, win, iters, variant, scr, merged):
 
 
 # (64, 1024) and (32, 2048): 9 and 18 strips of the warp-specialised kernel with h >= 16 (the benchmarked widths)
+@pytest.mark.parametrize("win", [5, 9])
 @pytest.mark.parametrize("shape,scale,n", [((96, 256), 1.0, 5), ((130, 372), 6.0, 5), ((64, 64), 3.0, 5),
-                                           ((64, 1024), 2.0, 40), ((32, 2048), 4.0, 3), ((50, 1000), 1.0, 2)])
-def test_flow_iteration_kernels_agree(eng, shape, scale, n):
-    """The warp-specialised kernel (k_flow_iter_ws, default for winsize 5) and the strip kernel (k_flow_iter, pinned
+                                           ((64, 1024), 2.0, 40), ((32, 2048), 4.0, 3), ((50, 1000), 1.0, 2),
+                                           ((16, 464), 2.0, 3), ((23, 480), 2.0, 3)])
+def test_flow_iteration_kernels_agree(eng, shape, scale, n, win):
+    """The warp-specialised kernel (k_flow_iter_ws, default for winsize 5 and 9) and the strip kernel (k_flow_iter, pinned
     against the oracle above) write the same bits, also for flows of many pixels (gathers far from the identity
     position, out-of-image lookups), with three iterations merged into one launch (ticketed work items, per-pair
     dependencies between the iterations) and over chained launches that reuse the scratch without clearing it."""
@@ -177,18 +179,19 @@ def test_flow_iteration_kernels_agree(eng, shape, scale, n):
     dR = dev(R_from_oracle_layout(R))
     nscr = eng.lib.fdn_flow_iteration_scratch_bytes(n, h, w)
     scr = torch.zeros(nscr, dtype=torch.uint8, device="cuda")
-    ref = _run_iterations(eng, dR, n, flow, h, w, 5, 3, 0, scr, merged=False)
+    ref = _run_iterations(eng, dR, n, flow, h, w, win, 3, 0, scr, merged=False)
     for iters, merged in ((3, True), (3, False), (3, True)):
-        got = _run_iterations(eng, dR, n, flow, h, w, 5, iters, 1, scr, merged)
+        got = _run_iterations(eng, dR, n, flow, h, w, win, iters, 1, scr, merged)
         assert np.array_equal(ref.view(np.int32), got.view(np.int32)), (iters, merged)
     # other iteration counts through the merged entry point (4 = 3 + 1 launches, 2, 1) against the strip kernel
     for iters in (1, 2, 4):
-        a = _run_iterations(eng, dR, n, flow, h, w, 5, iters, 0, scr, merged=True)
-        b = _run_iterations(eng, dR, n, flow, h, w, 5, iters, 1, scr, merged=True)
+        a = _run_iterations(eng, dR, n, flow, h, w, win, iters, 0, scr, merged=True)
+        b = _run_iterations(eng, dR, n, flow, h, w, win, iters, 1, scr, merged=True)
         assert np.array_equal(a.view(np.int32), b.view(np.int32)), iters
 
 
-def test_flow_iteration_ws_vs_oracle_wide(eng):
+@pytest.mark.parametrize("win", [5, 9])
+def test_flow_iteration_ws_vs_oracle_wide(eng, win):
     """k_flow_iter_ws on 9 strips (64 x 1024) against the oracle itself, not only against the strip kernel."""
     n, h, w = 2, 64, 1024
     imgs = images((h, w), 2 * n, 31)
@@ -200,11 +203,11 @@ def test_flow_iteration_ws_vs_oracle_wide(eng):
     nscr = eng.lib.fdn_flow_iteration_scratch_bytes(n, h, w)
     scr = torch.empty(nscr, dtype=torch.uint8, device="cuda")
     rc = eng.lib.fdn_flow_iteration(dR[:n].data_ptr(), dR[n:].data_ptr(), dev(flow).data_ptr(), out.data_ptr(), n, h, w,
-                                    5, scr.data_ptr(), nscr, None)
+                                    win, scr.data_ptr(), nscr, None)
     assert rc == 0, eng.lib.fdn_last_error()
     got = out.cpu().numpy()
     for i in range(n):
-        ref = O.blur_solve(O.update_matrices(R[i], R[n + i], flow[i]), 5)
+        ref = O.blur_solve(O.update_matrices(R[i], R[n + i], flow[i]), win)
         assert np.array_equal(got[i], ref), f"bit-equal fraction {np.mean(got[i] == ref)}"
 
 
