@@ -629,7 +629,12 @@ k_flow_iter_ws(WsArgs wa)
     };
 
     if (t >= NT) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+#ifndef FDN_WS_RC4
+#define FDN_WS_RC4 168
+#define FDN_WS_RS4 88
+#endif
+        if (MT == 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(FDN_WS_RS4));
+        else asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
         if (t >= NT + 32) {
             // =============================== solve warps: phase S ===============================
             // regularised 2x2 solve in float64, flow written once. Full tiles run as one straight-line block (the
@@ -790,7 +795,8 @@ k_flow_iter_ws(WsArgs wa)
     }
 
     // =============================== column warps: phase V ===============================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 176;");
+    if (MT == 4) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(FDN_WS_RC4));
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 176;");
     // thread t <-> tile position t <-> image column x0 - m - 1 + t (clamped: replicated border); threads beyond the
     // strip's halo work on a clamped column too, their results are never read
     const int xcl = min(max(x0 - m - 1 + t, 0), w - 1);
