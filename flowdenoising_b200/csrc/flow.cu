@@ -423,8 +423,12 @@ struct WsCfg {
     static constexpr int CWMAX = (NT - HALO) & ~3;
     static constexpr int NCH = (CWMAX + 31) / 32;   // 32-column chunks of a strip (scan -> solve hand-off)
     static constexpr int LS = NT + 2;       // tile line stride in doubles (even: every line is 16-byte aligned)
-    static constexpr size_t tiles_bytes = 2 * sizeof(double) * TR * 5 * LS + 128;   // two tiles (+ the scan's read-ahead past the last line)
-    static constexpr size_t smem_bytes = tiles_bytes + 8 * 2 * NCH + 16;      // + the chunk mbarriers, the ticket
+#ifndef FDN_WS_NBUF
+#define FDN_WS_NBUF 2
+#endif
+    static constexpr int NBUF = FDN_WS_NBUF;   // shared-memory tiles: phase V may run NBUF tiles ahead of the solve
+    static constexpr size_t tiles_bytes = NBUF * sizeof(double) * TR * 5 * LS + 128;   // (+ the scan's read-ahead past the last line)
+    static constexpr size_t smem_bytes = tiles_bytes + 8 * NBUF * NCH + 16;      // + the chunk mbarriers, the ticket
     static_assert(5 * TR <= 32, "phase H runs in one warp");
     static_assert(TR * TPP == RR && (TPP == 1 || TPP == 2), "a ring period is one tile or the two shared-memory tiles");
     static_assert(HALO + 8 <= 17, "the scan's register window spans two 8-column sets and one more column");
@@ -581,12 +585,12 @@ k_flow_iter_ws(WsArgs wa)
 {
     using C = WsCfg<MT, NT_>;
     constexpr int NT = C::NT, TR = C::TR, SR = C::SR, RR = C::RR, TPP = C::TPP, NB = C::NB, LS = C::LS, NCH = C::NCH, m = MT;
-    constexpr int BAR_FULL = 1, BAR_FREE = 5, BAR_SOLVED = 7;
+    constexpr int NBUF = C::NBUF, BAR_FULL = 1, BAR_FREE = 1 + NBUF, BAR_SOLVED = 1 + 2 * NBUF;
     constexpr unsigned WARPS = (NT + 128) / 32;
     extern __shared__ __align__(128) unsigned char smem_ws[];
     double* tiles = reinterpret_cast<double*>(smem_ws);                       // [2][TR*5][LS]
-    unsigned long long* chunk_bar = reinterpret_cast<unsigned long long*>(smem_ws + C::tiles_bytes);   // [2][NCH]
-    volatile int* sh = reinterpret_cast<volatile int*>(smem_ws + C::tiles_bytes + 8 * 2 * NCH);
+    unsigned long long* chunk_bar = reinterpret_cast<unsigned long long*>(smem_ws + C::tiles_bytes);   // [NBUF][NCH]
+    volatile int* sh = reinterpret_cast<volatile int*>(smem_ws + C::tiles_bytes + 8 * NBUF * NCH);
     const int h = wa.h, w = wa.w;
     const int t = threadIdx.x;
     const unsigned per_it = (unsigned)wa.n * (unsigned)wa.strips;
@@ -600,7 +604,7 @@ k_flow_iter_ws(WsArgs wa)
             while (ld_acquire_u32(dn) < (unsigned)wa.strips) __nanosleep(200);
         }
     }
-    if (t < 2 * NCH) mbar_init(smem_u32(chunk_bar + t), 1);
+    if (t < NBUF * NCH) mbar_init(smem_u32(chunk_bar + t), 1);
     __syncthreads();
     const unsigned ticket = (unsigned)sh[0];
     const int it = (int)(ticket / per_it);
@@ -657,15 +661,16 @@ k_flow_iter_ws(WsArgs wa)
             const int qlast = (ncols - 1) >> 5;
             for (int j = 0; j < ntiles; j++) {
                 const int y0 = j * TR;
-                const uint32_t bars = smem_u32(chunk_bar + (j & 1) * NCH);
-                const uint32_t parity = (uint32_t)((j >> 1) & 1);
+                const int buf = j % NBUF;
+                const uint32_t bars = smem_u32(chunk_bar + buf * NCH);
+                const uint32_t parity = (uint32_t)((j / NBUF) & 1);
                 // the solve follows the scan through the tile: 32-column chunk q goes to solve warp q % 3 as soon as the
                 // scan warp has passed it
                 for (int q = sw; q <= qlast; q += NS / 32) {
                     mbar_wait(bars + 8 * q, parity);
                     const int col = q * 32 + sln;
                     if (col < ncols && !FDN_WS_EXP(8)) {
-                        const double* tt = tiles + (j & 1) * TR * 5 * LS + col;
+                        const double* tt = tiles + buf * TR * 5 * LS + col;
                         float2* dst = fout + (int64_t)y0 * w + x0 + col;
                         if (y0 + TR <= h) {
 #pragma unroll
@@ -678,7 +683,7 @@ k_flow_iter_ws(WsArgs wa)
                 // a warp without a chunk in this strip (narrow strips) must not run ahead of the tile either: its
                 // arrival below has to count for THIS tile's phase of the FREE barrier
                 mbar_wait(bars + 8 * qlast, parity);
-                nbar_arrive(BAR_FREE + (j & 1), NS + NT);     // this warp is done with the tile (phase V of tile j+2 may overwrite it)
+                nbar_arrive(BAR_FREE + buf, NS + NT);     // this warp is done with the tile (phase V of tile j+NBUF may overwrite it)
             }
             if (it + 1 < wa.iters) {   // publish: this strip's flow of iteration `it` is in memory
                 nbar_sync(BAR_SOLVED, NS);
@@ -699,11 +704,12 @@ k_flow_iter_ws(WsArgs wa)
         static_assert(FDN_WS_HC == 8, "the sliding window below is written for 8-column chunks");
         for (int j = 0; j < ntiles; j++) {
             const int y = j * TR + r;
-            const uint32_t bars = smem_u32(chunk_bar + (j & 1) * NCH);
-            nbar_sync(BAR_FULL + (j & 1), NT + 32);
+            const int buf = j % NBUF;
+            const uint32_t bars = smem_u32(chunk_bar + buf * NCH);
+            nbar_sync(BAR_FULL + buf, NT + 32);
             const unsigned hmask = __ballot_sync(0xffffffffu, lane < 5 * TR && y < h);   // the scanning lanes
             if (lane < 5 * TR && y < h) {
-                double* line = tiles + ((j & 1) * TR * 5 + r * 5 + c) * LS;
+                double* line = tiles + (buf * TR * 5 + r * 5 + c) * LS;
                 double2* l2 = reinterpret_cast<double2*>(line);   // 16-byte aligned (LS is even)
                 // S(i) = S(i-1) + (vs[i+m] - vs[i-m-1]); S(i) overwrites the dead slot of column i-m-1.
                 // The line is read ONCE, 128 bits at a time, through a sliding window of two 8-column sets (plus, for
@@ -873,9 +879,9 @@ k_flow_iter_ws(WsArgs wa)
             const int j = jp + tp;
             if (TPP > 1 && j >= ntiles) break;
             const int y0 = j * TR;
-            const int buf = TPP > 1 ? tp : (j & 1);   // (jp is even when a period is two tiles)
+            const int buf = (TPP == 2 && NBUF == 2) ? tp : j % NBUF;   // (jp is even when a period is two tiles)
             double* tq = tiles + buf * TR * 5 * LS + t;
-            if (j >= 2) nbar_sync(BAR_FREE + buf, 96 + NT);   // tile j-2 has been solved: its shared-memory tile is free
+            if (j >= NBUF) nbar_sync(BAR_FREE + buf, 96 + NT);   // tile j-NBUF has been solved: its shared-memory tile is free
             // ---------------- phase V ----------------
 #pragma unroll
             for (int blk = 0; blk < NB; blk++) {
