@@ -60,6 +60,8 @@ def parse_args():
     ap.add_argument("--dtype", default=None, choices=["float32", "uint8"], help="input voxel type (values only: the filter runs in float32)")
     ap.add_argument("--no-of", action="store_true", help="OF disabled (plain separable Gaussian), as in cfg3")
     ap.add_argument("--fast-noof", action="store_true", help="no-OF path with float32 FMA arithmetic")
+    ap.add_argument("--recompute-flow", action="store_true",
+                    help="the reference's --recompute_flow: every flow starts from zero instead of the previous chain step")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-parity", action="store_true")
@@ -67,7 +69,7 @@ def parse_args():
     a = ap.parse_args()
     cfg = dict(CONFIGS[a.config])
     a.customised = any(v is not None for v in (a.shape, a.sigma, a.levels, a.winsize, a.dtype)) or \
-        (a.no_of and not cfg["no_of"])
+        (a.no_of and not cfg["no_of"]) or a.recompute_flow
     if a.shape is not None:
         cfg["shape"] = tuple(a.shape)
     if a.sigma is not None:
@@ -212,7 +214,8 @@ def cpu_reference_sample(vol_host, kernels, args, slices_per_axis, cores):
     {axis: (slice indices, oracle output slices)}): the slices are the bench's parity reference."""
     from oracle import fd_oracle as O
     Z, Y, X = vol_host.shape
-    o = O.OracleDenoiser(cores, vol_host, use_OF=not args.no_of, l=args.levels, w=args.winsize, backend="cv2")
+    o = O.OracleDenoiser(cores, vol_host, use_OF=not args.no_of, l=args.levels, w=args.winsize, backend="cv2",
+                         recompute_flow=args.recompute_flow)
     total = 0.0
     spent = 0.0
     slices = {}
@@ -293,11 +296,12 @@ def workload_config(args):
     kind = "uint8-valued (cast to float32 at load, like the reference's TIFF path)" if args.dtype == "uint8" else "float32"
     return {"workload": f"{Z}x{Y}x{X} {kind} FIB-SEM-like synthetic volume, {sig}, "
                         + ("OF disabled (plain separable Gaussian)" if args.no_of else
-                           f"Farneback levels={args.levels} winsize={args.winsize} iterations=3 poly_n=5 poly_sigma=1.2"),
+                           f"Farneback levels={args.levels} winsize={args.winsize} iterations=3 poly_n=5 poly_sigma=1.2"
+                           + (", --recompute_flow (no chained initial flow)" if args.recompute_flow else "")),
             "baseline_config": (f"BASELINE.json configs[{args.config_index}]" if not args.customised else
                                 f"custom (started from BASELINE.json configs[{args.config_index}])"),
             "shape": [Z, Y, X], "sigma": list(sg), "levels": args.levels, "winsize": args.winsize,
-            "input_dtype": args.dtype, "of": not args.no_of,
+            "input_dtype": args.dtype, "of": not args.no_of, "recompute_flow": bool(args.recompute_flow),
             "l2_policy": "inputs_exceed_l2 (volume and cached expansions are >> 126 MB)"
                          if Z * Y * X * 4 > (200 << 20) else "l2_flushed_between_steps (256 MiB device buffer rewritten)",
             "model_bytes_per_voxel": round(model_bytes_per_voxel((Z, Y, X), sg, args.levels, args.no_of), 1)}
@@ -343,7 +347,8 @@ def main():
     Z, Y, X = shape
     nvox = float(Z * Y * X)
     kernels = [gaussian_kernel(sg) for sg in args.sigma]
-    flow = None if args.no_of else FlowParams(levels=args.levels, winsize=args.winsize)
+    flow = None if args.no_of else FlowParams(levels=args.levels, winsize=args.winsize,
+                                              use_prev_flow=not args.recompute_flow)
     exact = not args.fast_noof
     integer = args.dtype == "uint8"
     eng = DeviceEngine(device)
@@ -489,7 +494,8 @@ def main():
         for i in range(1 + n_e2e):          # first one is warm-up
             h_vol[...] = pristine.numpy()   # filter() overwrites vol with the Z+Y intermediate (reference :289)
             obj = fd.GaussianDenoising(os.cpu_count(), h_vol) if args.no_of else \
-                fd.FlowDenoising(os.cpu_count(), h_vol, args.levels, args.winsize, fd.get_flow_with_prev_flow, fd.warp_slice)
+                fd.FlowDenoising(os.cpu_count(), h_vol, args.levels, args.winsize,
+                                 fd.get_flow_without_prev_flow if args.recompute_flow else fd.get_flow_with_prev_flow, fd.warp_slice)
             obj.exact = exact
             obj.filtered_vol = torch.empty(shape, dtype=torch.float32, pin_memory=True).numpy()
             torch.cuda.synchronize()
@@ -508,7 +514,8 @@ def main():
         try:
             pv = np.array(pristine.numpy())
             obj = fd.GaussianDenoising(os.cpu_count(), pv) if args.no_of else \
-                fd.FlowDenoising(os.cpu_count(), pv, args.levels, args.winsize, fd.get_flow_with_prev_flow, fd.warp_slice)
+                fd.FlowDenoising(os.cpu_count(), pv, args.levels, args.winsize,
+                                 fd.get_flow_without_prev_flow if args.recompute_flow else fd.get_flow_with_prev_flow, fd.warp_slice)
             obj.exact = exact
             torch.cuda.synchronize()
             t0 = time.perf_counter()
@@ -591,7 +598,8 @@ def hash_key(args, exact=True):
     Z, Y, X = args.shape
     sg = args.sigma
     return (f"{Z}x{Y}x{X}_{args.dtype}_s{sg[0]:g}-{sg[1]:g}-{sg[2]:g}_" +
-            ("noof_" + ("exact" if exact else "fast") if args.no_of else f"l{args.levels}w{args.winsize}"))
+            ("noof_" + ("exact" if exact else "fast") if args.no_of else
+             f"l{args.levels}w{args.winsize}" + ("_recompute" if args.recompute_flow else "")))
 
 
 if __name__ == "__main__":

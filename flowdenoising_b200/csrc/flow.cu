@@ -1197,7 +1197,22 @@ k_flow_area_down(const float2* __restrict__ in, int H, int W, float2* __restrict
     if (dx >= w) return;
     const float2* src = in + (int64_t)b * H * W;
     float rx, ry;
-    if (ax.fast && ay.fast) {
+    if (ax.fast && ay.fast && (ax.iscale & 3) == 0 && (W & 1) == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
+        // the same sum when a block row is a whole number of groups of four (every power-of-two pyramid): a group is two
+        // 16-byte loads, the accumulation order is unchanged (s += ((v0 + v1) + v2) + v3, groups in row-major order)
+        float sx_ = 0.f, sy_ = 0.f;
+        for (int sy = 0; sy < ay.iscale; sy++) {
+            const float4* row = reinterpret_cast<const float4*>(src + (int64_t)(dy * ay.iscale + sy) * W + dx * ax.iscale);
+            for (int g = 0; g < ax.iscale / 4; g++) {
+                const float4 q0 = __ldg(row + 2 * g), q1 = __ldg(row + 2 * g + 1);
+                sx_ = __fadd_rn(sx_, __fadd_rn(__fadd_rn(__fadd_rn(q0.x, q0.z), q1.x), q1.z));
+                sy_ = __fadd_rn(sy_, __fadd_rn(__fadd_rn(__fadd_rn(q0.y, q0.w), q1.y), q1.w));
+            }
+        }
+        const float inv = __fdiv_rn(1.f, (float)(ax.iscale * ay.iscale));
+        rx = __fmul_rn(sx_, inv);
+        ry = __fmul_rn(sy_, inv);
+    } else if (ax.fast && ay.fast) {
         // resizeAreaFast_: block sum in row-major order, unrolled by four, times 1/area (float32)
         const int area = ax.iscale * ay.iscale;
         float sx_ = 0.f, sy_ = 0.f;

@@ -352,19 +352,45 @@ class GaussianDenoising():
     def filter_along_Y_slice(self, y, kernel): self._slice(1, y, kernel)
     def filter_along_X_slice(self, x, kernel): self._slice(2, x, kernel)
 
+    def _chunk(self, axis, start, count, kernel):
+        '''The reference's unit of parallel work (:160-173) as ONE device call: the chunk's slices plus an r-slice
+        periodic halo go up as a slab, one non-periodic view filters them, the result comes back. Same bits as
+        slice-by-slice calls (every output slice sees the same inputs).'''
+        if count <= 0:
+            return
+        eng = _get_engine()
+        torch = eng.torch
+        kernel = np.asarray(kernel, dtype=np.float64)
+        assert kernel.size % 2 != 0
+        r = kernel.size // 2
+        n = self.vol.shape[axis]
+        idxs = [(start + d) % n for d in range(-r, count + r)]
+        slab = np.ascontiguousarray(np.moveaxis(np.take(self.vol, idxs, axis=axis), axis, 0), dtype=np.float32)
+        d_in = torch.from_numpy(slab).to(eng.device)
+        H, W = slab.shape[1:]
+        d_out = torch.empty((count, H, W), dtype=torch.float32, device=eng.device)
+        v = _engine.View(count + 2 * r, count, r, 0, H, W, H * W, W, H * W, W)
+        eng.filter_view(d_in, d_out, v, kernel, self._flow(), exact=self.exact)
+        res = d_out.cpu().numpy()
+        out_idx = [(start + d) % n for d in range(count)]
+        if axis == 0:
+            self.filtered_vol[out_idx, :, :] = res
+        elif axis == 1:
+            self.filtered_vol[:, out_idx, :] = np.moveaxis(res, 0, 1)
+        else:
+            self.filtered_vol[:, :, out_idx] = np.moveaxis(res, 0, 2)
+        self.progress += count
+
     def filter_along_Z_chunk(self, chunk_index, chunk_size, chunk_offset, kernel):
-        for z in range(chunk_size):
-            self.filter_along_Z_slice(chunk_index*chunk_size + z + chunk_offset, kernel)
+        self._chunk(0, chunk_index*chunk_size + chunk_offset, chunk_size, kernel)
         return chunk_index
 
     def filter_along_Y_chunk(self, chunk_index, chunk_size, chunk_offset, kernel):
-        for y in range(chunk_size):
-            self.filter_along_Y_slice(chunk_index*chunk_size + y + chunk_offset, kernel)
+        self._chunk(1, chunk_index*chunk_size + chunk_offset, chunk_size, kernel)
         return chunk_index
 
     def filter_along_X_chunk(self, chunk_index, chunk_size, chunk_offset, kernel):
-        for x in range(chunk_size):
-            self.filter_along_X_slice(chunk_index*chunk_size + x + chunk_offset, kernel)
+        self._chunk(2, chunk_index*chunk_size + chunk_offset, chunk_size, kernel)
         return chunk_index
 
     def filter(self, kernels):

@@ -229,6 +229,24 @@ def test_module_surface_drop_in(golden):
     obj3 = fd.FlowDenoising(1, vol.copy(), int(g["l"]), int(g["w"]))
     obj3.filter_along_Z_slice(3, kernels[0])
     check_of("module Z slice 3", obj3.filtered_vol[3], g["Z"][3])
+    # per-chunk entry points (reference :160-173): one device call per chunk, chunks tile the axis like the reference's
+    # pool.starmap arguments (chunk_index, chunk_size, chunk_offset)
+    obj4 = fd.FlowDenoising(2, vol.copy(), int(g["l"]), int(g["w"]))
+    Z, Y, X = vol.shape
+    cs = Z // 2
+    assert obj4.filter_along_Z_chunk(0, cs, 0, kernels[0]) == 0
+    assert obj4.filter_along_Z_chunk(1, cs, 0, kernels[0]) == 1
+    obj4.filter_along_Z_chunk(0, Z - 2 * cs, 2 * cs, kernels[0])      # the remainder chunk (:190-192)
+    check_of("module Z chunks", obj4.filtered_vol, g["Z"])
+    assert obj4.progress == Z
+    obj5 = fd.FlowDenoising(2, vol.copy(), int(g["l"]), int(g["w"]))
+    obj5.filter_along_Y_chunk(0, Y, 0, kernels[1])
+    obj6 = fd.FlowDenoising(2, vol.copy(), int(g["l"]), int(g["w"]))
+    obj6.filter_along_Y(kernels[1])
+    assert np.array_equal(obj5.filtered_vol, obj6.filtered_vol)
+    obj5.filter_along_X_chunk(1, 3, 2, kernels[2])
+    obj6.filter_along_X(kernels[2])
+    assert np.array_equal(obj5.filtered_vol[:, :, 5:8], obj6.filtered_vol[:, :, 5:8])
     n = golden("toy_noof.npz")
     gd = fd.GaussianDenoising(2, n["vol"].astype(np.float32))
     assert np.array_equal(gd.filter(kernels), n["ZYX"])
