@@ -362,17 +362,32 @@ def main():
             torch.cuda.synchronize()
 
     # ---- workload (device resident before the timed region) ----
+    # Volumes of more than 2^31 voxels (cfg5) are never synthesised in one piece: they are DEFINED as eight Z-slabs,
+    # slab i generated with seed 1 + i, so that 1, 2, 4 and 8 ranks see the same volume and their result hashes compare
+    big = Z * Y * X > (1 << 31)
+
+    def big_slab(z0, z1):
+        if Z % 8 or z0 % (Z // 8) or z1 % (Z // 8):      # other splits: a private slab per rank (hashes not comparable)
+            return synthetic_volume_torch((z1 - z0, Y, X), device, seed=1 + rank, integer=integer)
+        zs = Z // 8
+        out = torch.empty((z1 - z0, Y, X), dtype=torch.float32, device=device)
+        for i in range(z0 // zs, z1 // zs):
+            out[i * zs - z0:(i + 1) * zs - z0] = synthetic_volume_torch((zs, Y, X), device, seed=1 + i, integer=integer)
+        return out
+
     if world == 1:
-        d_vol = synthetic_volume_torch(shape, device, seed=1, integer=integer)
+        d_vol = big_slab(0, Z) if big else synthetic_volume_torch(shape, device, seed=1, integer=integer)
         run_once = lambda: eng.filter(d_vol, kernels, flow, exact=exact)
     else:
         from flowdenoising_b200.dist import DistributedDenoiser
         dd = DistributedDenoiser(eng, shape, flow, exact=exact)
         z0, z1 = dd.z_range
-        full_seeded = synthetic_volume_torch(shape, device, seed=1, integer=integer) if Z * Y * X <= (1 << 31) else None
-        d_slab = full_seeded[z0:z1].contiguous() if full_seeded is not None else \
-            synthetic_volume_torch((z1 - z0, Y, X), device, seed=1 + rank, integer=integer)
-        del full_seeded
+        if big:
+            d_slab = big_slab(z0, z1)
+        else:
+            full_seeded = synthetic_volume_torch(shape, device, seed=1, integer=integer)
+            d_slab = full_seeded[z0:z1].contiguous()
+            del full_seeded
         run_once = lambda: dd.filter(d_slab, kernels)
 
     def runner():
@@ -381,7 +396,9 @@ def main():
         return run_once()
 
     # ---- device-resident throughput (`value`) ----
+    res = None
     for _ in range(args.warmup):
+        res = None          # drop the previous step's volumes before the next step allocates its own
         res = runner()
     barrier()
     sampler = ClockSampler(physical_gpu_index(local_rank))
@@ -394,6 +411,7 @@ def main():
     barrier()
     ev0.record()
     for _ in range(args.steps):
+        res = None
         res = runner()
     ev1.record()
     barrier()
