@@ -36,6 +36,9 @@ SIGNATURES = {
     "fdn_last_error": (C.c_char_p, []),
     "fdn_launch_count": (c_i64, []),
     "fdn_reset_launch_count": (None, []),
+    "fdn_launch_log_enable": (None, [C.c_int]),
+    "fdn_launch_log_count": (C.c_int, []),
+    "fdn_launch_log_name": (C.c_char_p, [C.c_int]),
     "fdn_progress_milli": (c_i64, []),
     "fdn_progress_reset": (None, []),
     "fdn_profile_enable": (None, [C.c_int]),

@@ -22,6 +22,16 @@ namespace fdn {
 static thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launches{0};
 
+// launch log: the names of the kernels launched while it is enabled (tests assert which specialisation a level uses)
+std::atomic<bool> g_launch_log_on{false};
+static std::mutex g_launch_log_mutex;
+static std::vector<const char*> g_launch_log;
+void launch_log_add(const char* name)
+{
+    std::lock_guard<std::mutex> lock(g_launch_log_mutex);
+    if (g_launch_log.size() < (1u << 20)) g_launch_log.push_back(name);
+}
+
 void set_error(const char* fmt, ...)
 {
     va_list ap;
@@ -341,6 +351,23 @@ int64_t fdn_launch_count(void) { return g_launches.load(); }
 int64_t fdn_progress_milli(void) { return (int64_t)g_progress_milli.load(); }
 void fdn_progress_reset(void) { g_progress_milli.store(0); }
 void fdn_reset_launch_count(void) { g_launches.store(0); }
+
+void fdn_launch_log_enable(int on)
+{
+    std::lock_guard<std::mutex> lock(g_launch_log_mutex);
+    if (on) g_launch_log.clear();
+    g_launch_log_on.store(on != 0);
+}
+int fdn_launch_log_count(void)
+{
+    std::lock_guard<std::mutex> lock(g_launch_log_mutex);
+    return (int)g_launch_log.size();
+}
+const char* fdn_launch_log_name(int i)
+{
+    std::lock_guard<std::mutex> lock(g_launch_log_mutex);
+    return (i >= 0 && i < (int)g_launch_log.size()) ? g_launch_log[i] : "";
+}
 
 void fdn_profile_enable(int on) { g_prof_on = on != 0; }
 

@@ -13,6 +13,8 @@ namespace fdn {
 // ---- error plumbing (no exceptions across the C ABI) ----
 void set_error(const char* fmt, ...);
 extern std::atomic<int64_t> g_launches;   // (engines on several host threads may launch concurrently)
+extern std::atomic<bool> g_launch_log_on;
+void launch_log_add(const char* name);    // records the kernel name while the launch log is enabled (tests)
 
 #define FDN_CHECK_ARG(cond, ...)                 \
     do {                                         \
@@ -36,6 +38,7 @@ extern std::atomic<int64_t> g_launches;   // (engines on several host threads ma
 #define FDN_LAUNCHED(name)                                                                      \
     do {                                                                                        \
         ++fdn::g_launches;                                                                      \
+        if (fdn::g_launch_log_on.load(std::memory_order_relaxed)) fdn::launch_log_add(name);    \
         cudaError_t e_ = cudaGetLastError();                                                    \
         if (e_ != cudaSuccess) {                                                                \
             fdn::set_error("launch of %s failed at %s:%d: %s", name, __FILE__, __LINE__,        \

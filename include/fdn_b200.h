@@ -73,6 +73,11 @@ const char* fdn_last_error(void);
 /* Number of this library's kernel launches since the last reset (bench.py "gpu_launches"). */
 int64_t fdn_launch_count(void);
 void fdn_reset_launch_count(void);
+/* Launch log (tests): while enabled, the name of every kernel this library launches is recorded in order, so that a
+ * test can assert which specialisation a pyramid level / window size actually runs. Enabling clears the log. */
+void fdn_launch_log_enable(int on);
+int fdn_launch_log_count(void);
+const char* fdn_launch_log_name(int i);
 /* Progress feedback for the reference's feedback() thread (src/flowdenoising.py:139-140, :292-295): thousandths of
  * output slices the device has finished since the last reset, all passes of this process together. A pass advances it
  * after every chain step (host functions in the stream), so it follows execution, not enqueueing. fdn_gauss_rows

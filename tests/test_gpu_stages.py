@@ -307,3 +307,49 @@ def test_transpose(eng):
     a = rng.standard_normal((5, 37, 70)).astype(np.float32)
     out = eng.transpose_yx(dev(a))
     assert np.array_equal(out.cpu().numpy(), np.transpose(a, (0, 2, 1)))
+
+
+def _launch_names(lib):
+    return [lib.fdn_launch_log_name(i).decode() for i in range(lib.fdn_launch_log_count())]
+
+
+def test_levels_launch_their_specialised_kernels(eng):
+    """Which kernel a pyramid level / window size really launches (round 1 shipped register-window blurs for 7 and 17
+    taps while the pyramid uses 9 and 19: dead code). The benchmarked slice sizes must take the specialised paths:
+    4-outputs-per-thread blurs for every level's tap count, the TMA polynomial expansion, the exact-x2 upsample and
+    the warp-specialised flow iteration for winsize 5 and 9; other window sizes take the strip kernel."""
+    from flowdenoising_b200.engine import FlowParams, level_geometry
+    lib = eng.lib
+    for (H, W, levels, win) in [(256, 1024, 3, 5), (512, 2048, 5, 9), (96, 512, 3, 7)]:
+        geo = level_geometry(H, W, levels)
+        assert [g[2] for g in geo] == [3, 3, 9, 19, 39, 79][:len(geo)]      # smoothing taps per level (SURVEY App. A.0-2)
+        assert len(geo) == {3: 4, 5: 5}[levels] if H >= 256 else len(geo) == 2
+        v = images((H, W), 2, 41)
+        flow = torch.zeros((1, H, W, 2), dtype=torch.float32, device="cuda")
+        lib.fdn_launch_log_enable(1)
+        eng.farneback(dev(v[0:1]), dev(v[1:2]), flow, FlowParams(levels, win, 3, 5, 1.2, True))
+        torch.cuda.synchronize()
+        lib.fdn_launch_log_enable(0)
+        names = _launch_names(lib)
+        nl = len(geo)
+        assert names.count("k_blur_rows4") == 2 * nl and names.count("k_blur_cols4") == 2 * nl, names
+        assert "k_blur_rows" not in names and "k_blur_cols" not in names
+        assert names.count("k_polyexp_tma") == 2 * nl and "k_polyexp" not in names
+        assert names.count("k_flow_upsample_x2") == nl - 1 and "k_flow_upsample" not in names
+        if win in (5, 9):
+            ws_levels = sum(1 for (h, w, _k, _s) in geo if w >= 64 and h >= 16 and w % 4 == 0)
+            assert names.count("k_flow_iter_ws") == ws_levels, names           # one launch = the three iterations
+            assert names.count("k_flow_iter") == 3 * (nl - ws_levels)
+        else:
+            assert names.count("k_flow_iter") == 3 * nl and "k_flow_iter_ws" not in names
+    # a whole OF pass: both chain directions of a chain step in ONE warp kernel launch, one finishing launch per chunk
+    vol = dev(images((64, 256), 12, 43))
+    out = torch.empty_like(vol)
+    lib.fdn_launch_log_enable(1)
+    eng.filter_along_axis(vol, out, 0, O.get_gaussian_kernel(1.0), FlowParams())
+    torch.cuda.synchronize()
+    lib.fdn_launch_log_enable(0)
+    names = _launch_names(lib)
+    r = 4   # sigma 1 -> 9 taps
+    assert names.count("k_warp_pair") == r and names.count("k_acc_finish") == 1 and "k_warp_acc" not in names
+    assert lib.fdn_launch_log_count() == len(names) and lib.fdn_launch_log_name(10 ** 6) == b""
