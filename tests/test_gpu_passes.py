@@ -262,10 +262,13 @@ def test_module_surface_drop_in(golden):
         obj.filter_along_Z(np.ones(4) / 4)      # even kernel: same assert as the reference (:309)
 
 
-@pytest.mark.parametrize("shape,sigmas,lw", [((7, 45, 67), (0.5, 1.0, 0.5), (3, 5)), ((9, 70, 53), (1.0, 0.5, 0.5), (2, 7))])
+@pytest.mark.parametrize("shape,sigmas,lw", [((7, 45, 67), (0.5, 1.0, 0.5), (3, 5)), ((9, 70, 53), (1.0, 0.5, 0.5), (2, 7)),
+                                             ((5, 45, 67), (1.5, 0.5, 0.5), (3, 5)), ((3, 64, 64), (1.0, 0.5, 0.5), (3, 9))])
 def test_of_odd_shapes_vs_c_oracle(eng, shape, sigmas, lw):
     """Odd sizes (non-power-of-two pyramid levels, partial strips/tiles, scalar tails of the blur): every pass equals
-    the C oracle (itself bit-exact vs cv2) bit for bit."""
+    the C oracle (itself bit-exact vs cv2) bit for bit. The last two volumes are SHORTER than the kernel along Z
+    (13 taps on 5 slices, 9 taps on 3): the reference's `% shape` (:312, :320) then wraps more than once and a slice
+    meets itself as its own neighbour."""
     from flowdenoising_b200.engine import FlowParams
     vol = O.synthetic_volume(shape, seed=61, noise_sigma=8.0)
     p = FlowParams(lw[0], lw[1])
