@@ -71,6 +71,7 @@ struct ProfScope {
 struct PolyConsts {
     int n;
     float g[8], xg[8], xxg[8];  // taps k = 0..n (n <= 7)
+    double gd[8], xxgd[8];      // (double)g[k], (double)xxg[k]: the horizontal pass multiplies them in float64
     double ig11, ig03, ig33, ig55;
 };
 void prepare_poly_consts(int n, double sigma, PolyConsts* pc);

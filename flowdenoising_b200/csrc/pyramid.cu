@@ -109,6 +109,7 @@ void prepare_poly_consts(int n, double sigma, PolyConsts* pc)
     pc->ig55 = inv[5][5];
     for (int k = 0; k < 8; k++) { pc->g[k] = pc->xg[k] = pc->xxg[k] = 0.f; }
     for (int k = 0; k <= n; k++) { pc->g[k] = g[n + k]; pc->xg[k] = xg[n + k]; pc->xxg[k] = xxg[n + k]; }
+    for (int k = 0; k < 8; k++) { pc->gd[k] = (double)pc->g[k]; pc->xxgd[k] = (double)pc->xxg[k]; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -405,8 +406,8 @@ k_polyexp(const float* __restrict__ img, int64_t img_stride, float* __restrict__
         for (int k = 1; k <= n; k++) {
             double tg = (double)__fadd_rn(r0[k], r0[-k]);
             g0 = pc.g[k];
-            b1 = __dadd_rn(b1, __dmul_rn(tg, (double)g0));
-            b4 = __dadd_rn(b4, __dmul_rn(tg, (double)pc.xxg[k]));
+            b1 = __dadd_rn(b1, __dmul_rn(tg, pc.gd[k]));
+            b4 = __dadd_rn(b4, __dmul_rn(tg, pc.xxgd[k]));
             b2 = __dadd_rn(b2, (double)__fmul_rn(__fsub_rn(r0[k], r0[-k]), pc.xg[k]));
             b3 = __dadd_rn(b3, (double)__fmul_rn(__fadd_rn(r1[k], r1[-k]), g0));
             b6 = __dadd_rn(b6, (double)__fmul_rn(__fsub_rn(r1[k], r1[-k]), pc.xg[k]));
@@ -537,8 +538,8 @@ k_polyexp_tma(const __grid_constant__ CUtensorMap tmap, float* __restrict__ R, i
             for (int k = 1; k <= n; k++) {
                 const double tg = (double)__fadd_rn(r0[k], r0[-k]);
                 g0 = pc.g[k];
-                b1 = __dadd_rn(b1, __dmul_rn(tg, (double)g0));
-                b4 = __dadd_rn(b4, __dmul_rn(tg, (double)pc.xxg[k]));
+                b1 = __dadd_rn(b1, __dmul_rn(tg, pc.gd[k]));
+                b4 = __dadd_rn(b4, __dmul_rn(tg, pc.xxgd[k]));
                 b2 = __dadd_rn(b2, (double)__fmul_rn(__fsub_rn(r0[k], r0[-k]), pc.xg[k]));
                 b3 = __dadd_rn(b3, (double)__fmul_rn(__fadd_rn(r1[k], r1[-k]), g0));
                 b6 = __dadd_rn(b6, (double)__fmul_rn(__fsub_rn(r1[k], r1[-k]), pc.xg[k]));
