@@ -539,6 +539,13 @@ __device__ __forceinline__ void ws_diffs(double (&D)[8], const double2 (&W0)[4],
 #ifndef FDN_WS_L2PF
 #define FDN_WS_L2PF 0
 #endif
+#ifndef FDN_WS_SOLVE_SLEEP
+// The solve warps sleep this many nanoseconds between two tries of a chunk mbarrier. A bare try_wait loop retries every
+// ~40 cycles: measured, a sixth of all warp instructions the kernel issued were that spin. Pauses of 20 .. 400 ns leave
+// the launch time unchanged (2.197 .. 2.200 ms per iteration, 128 pairs of 1024 x 1024) and take the spin out of the
+// issue arbitration and the power budget.
+#define FDN_WS_SOLVE_SLEEP 100
+#endif
 #define FDN_WS_MAX_ITERS 3   // iterations per launch: one flow buffer per iteration, none read after being rewritten
 
 struct WsArgs {
@@ -667,7 +674,7 @@ k_flow_iter_ws(WsArgs wa)
                 // the solve follows the scan through the tile: 32-column chunk q goes to solve warp q % 3 as soon as the
                 // scan warp has passed it
                 for (int q = sw; q <= qlast; q += NS / 32) {
-                    mbar_wait(bars + 8 * q, parity);
+                    mbar_wait_sleep<FDN_WS_SOLVE_SLEEP>(bars + 8 * q, parity);
                     const int col = q * 32 + sln;
                     if (col < ncols && !FDN_WS_EXP(8)) {
                         const double* tt = tiles + buf * TR * 5 * LS + col;
@@ -682,7 +689,7 @@ k_flow_iter_ws(WsArgs wa)
                 }
                 // a warp without a chunk in this strip (narrow strips) must not run ahead of the tile either: its
                 // arrival below has to count for THIS tile's phase of the FREE barrier
-                mbar_wait(bars + 8 * qlast, parity);
+                mbar_wait_sleep<FDN_WS_SOLVE_SLEEP>(bars + 8 * qlast, parity);
                 nbar_arrive(BAR_FREE + buf, NS + NT);     // this warp is done with the tile (phase V of tile j+NBUF may overwrite it)
             }
             if (it + 1 < wa.iters) {   // publish: this strip's flow of iteration `it` is in memory
