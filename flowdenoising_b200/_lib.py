@@ -64,6 +64,8 @@ SIGNATURES = {
                                         C.c_void_p]),
     "fdn_copy3d": (C.c_int, [c_f32p, c_i64, c_i64, C.c_int, C.c_int, C.c_int, C.c_int, c_f32p, c_i64, c_i64, C.c_int,
                              C.c_int, C.c_int, C.c_void_p]),
+    "fdn_copy2d_async": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int,
+                                   C.c_void_p]),
     "fdn_pyramid_level": (C.c_int, [c_f32p, C.c_int, C.c_int, C.c_int, c_i64, c_i64, C.c_int, C.c_double, C.c_int,
                                     C.c_int, c_f32p, c_f32p, C.c_void_p]),
     "fdn_polyexp": (C.c_int, [c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, c_f32p, C.c_void_p]),

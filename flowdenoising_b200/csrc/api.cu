@@ -238,7 +238,9 @@ static int make_plan(const fdn_view& v, int klen, const fdn_of_params& of, int c
     FDN_CHECK_ARG(v.n_in >= 1 && v.n_out >= 1 && v.H >= 1 && v.W >= 1, "empty view");
     p->r = klen / 2;
     if (v.periodic) {
-        FDN_CHECK_ARG(v.halo == 0 && v.n_in == v.n_out, "periodic views must have halo == 0 and n_in == n_out");
+        FDN_CHECK_ARG(v.halo >= 0 && v.halo < v.n_in && v.n_out <= v.n_in,
+                      "periodic views need 0 <= halo < n_in and n_out <= n_in (halo=%d, n_in=%d, n_out=%d)", v.halo,
+                      v.n_in, v.n_out);
     } else {
         FDN_CHECK_ARG(v.halo >= p->r && v.n_in >= v.n_out + v.halo + p->r,
                       "non-periodic view needs >= r halo slices on both sides (r=%d, halo=%d, n_in=%d, n_out=%d)",
@@ -514,7 +516,9 @@ int fdn_gauss_axis(const float* d_in, float* d_out, const fdn_view* view, const 
     FDN_CHECK_ARG(d_in && d_out && view && kernel, "null argument");
     const fdn_view& v = *view;
     FDN_CHECK_ARG(klen >= 1 && (klen & 1), "kernel length must be odd");
-    if (v.periodic) FDN_CHECK_ARG(v.halo == 0 && v.n_in == v.n_out, "periodic views must have halo == 0");
+    FDN_CHECK_ARG(v.n_in >= 1 && v.n_out >= 1 && v.H >= 1 && v.W >= 1, "empty view");
+    if (v.periodic) FDN_CHECK_ARG(v.halo >= 0 && v.halo < v.n_in && v.n_out <= v.n_in,
+                                  "periodic views need 0 <= halo < n_in and n_out <= n_in");
     else FDN_CHECK_ARG(v.halo >= klen / 2 && v.n_in >= v.n_out + v.halo + klen / 2, "halo too small");
     int rc = launch_gauss_axis(d_in, d_out, v, kernel, klen, exact, static_cast<cudaStream_t>(stream));
     if (rc == FDN_OK) progress_add(static_cast<cudaStream_t>(stream), 1000ll * v.n_out);
@@ -548,6 +552,19 @@ int fdn_copy3d(const float* d_in, int64_t in_sa, int64_t in_sb, int b0, int b_wr
     FDN_CHECK_ARG(d_in && d_out && A >= 1 && B >= 1 && C >= 1, "bad argument");
     return launch_copy3d(d_in, in_sa, in_sb, b0, b_wrap, c0, c_wrap, d_out, out_sa, out_sb, A, B, C,
                          static_cast<cudaStream_t>(stream));
+}
+
+int fdn_copy2d_async(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes, size_t rows,
+                     int direction, void* stream)
+{
+    FDN_CHECK_ARG(dst && src && width_bytes >= 1 && rows >= 1 && dst_pitch >= width_bytes && src_pitch >= width_bytes,
+                  "bad argument");
+    FDN_CHECK_ARG(direction >= 0 && direction <= 2, "direction must be 0 (host to device), 1 (device to host) or 2");
+    const cudaMemcpyKind kind = direction == 0 ? cudaMemcpyHostToDevice
+                              : direction == 1 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    FDN_CUDA(cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, width_bytes, rows, kind,
+                               static_cast<cudaStream_t>(stream)));
+    return FDN_OK;
 }
 
 int fdn_pyramid_level(const float* d_img, int n, int H, int W, int64_t slice_stride, int64_t row_stride, int ksz,

@@ -115,6 +115,19 @@ class DeviceEngine:
                 hi = mid - 1
         return lo
 
+    def reserve_workspace(self, view: View, klen: int, flow: Optional[FlowParams]):
+        """Sizes the workspace for a later filter_view(view) now, so that a smaller call issued first (the head of a
+        pass that overlaps the upload) does not allocate a workspace the next call has to replace."""
+        if flow is None:
+            return
+        with self.torch.cuda.device(self.device):
+            ofp = flow.c_struct()
+            chunk = self._pick_chunk(view, klen, ofp)
+            nbytes = self.lib.fdn_workspace_bytes(C.byref(view), klen, C.byref(ofp), int(chunk))
+            if nbytes == 0:
+                _lib.check(1)
+            self._workspace(nbytes)
+
     # ---- one pass over an explicit view ----
     def filter_view(self, d_in, d_out, view: View, kernel, flow: Optional[FlowParams], chunk: Optional[int] = None,
                     exact: bool = True):

@@ -175,6 +175,176 @@ def _to_host(t, dst, torch):
         dst[...] = t.cpu().numpy()
 
 
+# In-core volumes of at least this many bytes run the first slices of the Z pass and the last columns of the X pass
+# as device calls of their own (windows of the periodic view, include/fdn_b200.h), so that the rest of the upload and
+# most of the download overlap the passes. Smaller volumes are not worth the two extra calls.
+_OVERLAP_MIN_BYTES = 256 << 20
+_TRACE = None   # development (tools/overlap_lab.py): a list that receives (label, CUDA event) stamps of filter()
+
+
+def _mark(torch, label):
+    if _TRACE is not None:
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        _TRACE.append((label, e, time.perf_counter()))
+
+
+class _Upload:
+    """Host volume -> float32 device tensor `d` on a side stream, the Z ranges in the given order. ready(k) makes the
+    current stream wait until ranges 0..k are on the device. A pinned float32 array is copied directly; anything else
+    goes through the two pinned staging buffers on a host thread (cast + copy of one piece overlapping the DMA of
+    the previous one)."""
+
+    def __init__(self, vol, torch, dev, ranges):
+        self.torch = torch
+        shape = tuple(int(s) for s in vol.shape)
+        self.d = torch.empty(shape, dtype=torch.float32, device=dev)
+        self.stream = torch.cuda.Stream(device=dev)
+        self.stream.wait_stream(torch.cuda.current_stream())   # earlier users of this memory are done first
+        self.events = [torch.cuda.Event() for _ in ranges]
+        self.flags = [threading.Event() for _ in ranges]
+        self.error = None
+        self.thread = None
+        if _is_pinned_f32(vol, torch):
+            src = torch.from_numpy(vol)
+            with torch.cuda.stream(self.stream):
+                for k, (z0, z1) in enumerate(ranges):
+                    if z1 > z0:
+                        self.d[z0:z1].copy_(src[z0:z1], non_blocking=True)
+                    self.events[k].record(self.stream)
+                    self.flags[k].set()
+        else:
+            self.thread = threading.Thread(target=self._feed, args=(vol, list(ranges)), daemon=True)
+            self.thread.start()
+
+    def _feed(self, vol, ranges):
+        torch = self.torch
+        try:
+            shape = tuple(self.d.shape)
+            plane = int(np.prod(shape[1:]))
+            step = max(1, (_STAGE_BYTES // 4) // plane)
+            bufs = _pinned_pair(torch)
+            evs = [None, None]
+            i = 0
+            with torch.cuda.device(self.d.device), torch.cuda.stream(self.stream):
+                for k, (a, b) in enumerate(ranges):
+                    for z0 in range(a, b, step):
+                        z1 = min(b, z0 + step)
+                        buf = bufs[i & 1][:(z1 - z0) * plane].view((z1 - z0,) + shape[1:])
+                        if evs[i & 1] is not None:
+                            evs[i & 1].synchronize()
+                        np.copyto(buf.numpy(), vol[z0:z1], casting="unsafe")
+                        self.d[z0:z1].copy_(buf, non_blocking=True)
+                        evs[i & 1] = torch.cuda.Event()
+                        evs[i & 1].record(self.stream)
+                        i += 1
+                    self.events[k].record(self.stream)
+                    self.flags[k].set()
+                for e in evs:                  # the staging buffers belong to the next caller after this
+                    if e is not None:
+                        e.synchronize()
+        except BaseException as e:             # surfaces in ready() / close() on the calling thread
+            self.error = e
+            for f in self.flags:
+                f.set()
+
+    def ready(self, k):
+        self.flags[k].wait()
+        if self.error is not None:
+            raise self.error
+        self.torch.cuda.current_stream().wait_event(self.events[k])
+
+    def close(self):
+        if self.thread is not None:
+            self.thread.join()
+        if self.error is not None:
+            raise self.error
+
+
+def _prefault(a):
+    """Touches every page of a freshly allocated (np.zeros_like: still unmapped) result array on a host thread while
+    the device computes, so that the download's host copy does not pay the page faults. Values are unchanged."""
+    def touch():
+        try:
+            flat = a.reshape(-1)
+            step = max(1, 4096 // a.itemsize)
+            for i in range(0, flat.size, step << 14):      # 64 MB at a time: short slices keep the GIL available
+                seg = flat[i:i + (step << 14):step]
+                seg[...] = seg.copy()                      # (NumPy skips a plain self-assignment)
+        except Exception:
+            pass                                            # an optimisation only
+    if not (isinstance(a, np.ndarray) and a.flags.c_contiguous and a.flags.writeable):
+        return None
+    th = threading.Thread(target=touch, daemon=True)
+    th.start()
+    return th
+
+
+class _DownloadCols:
+    """Columns [x0, x1) of a device volume [Z, Y, X] -> the same columns of the caller's array, on a side stream
+    (pitched copies, fdn_copy2d_async), while the main stream goes on with the other columns."""
+
+    def __init__(self, t, dst, x0, x1, torch):
+        self.torch = torch
+        self.t, self.dst, self.x0, self.x1 = t, dst, int(x0), int(x1)
+        self.stream = torch.cuda.Stream(device=t.device)
+        self.ready = torch.cuda.Event()
+        self.ready.record()                      # on the current stream: the columns are complete after this point
+        self.thread = None
+        self.error = None
+        Z, Y, X = (int(v) for v in t.shape)
+        if _is_pinned_f32(dst, torch):
+            lib = _engine._lib.load()
+            with torch.cuda.device(t.device):
+                self.stream.wait_event(self.ready)
+                _engine._lib.check(lib.fdn_copy2d_async(
+                    dst.ctypes.data + 4 * self.x0, 4 * X, t.data_ptr() + 4 * self.x0, 4 * X, 4 * (self.x1 - self.x0),
+                    Z * Y, 1, self.stream.cuda_stream))
+        else:
+            self.thread = threading.Thread(target=self._drain, daemon=True)
+            self.thread.start()
+
+    def _drain(self):
+        torch = self.torch
+        try:
+            lib = _engine._lib.load()
+            t, dst, x0, x1 = self.t, self.dst, self.x0, self.x1
+            Z, Y, X = (int(v) for v in t.shape)
+            w = x1 - x0
+            step = max(1, (_STAGE_BYTES // 4) // (Y * w))
+            bufs = [torch.empty(_STAGE_BYTES // 4, dtype=torch.float32, pin_memory=True) for _ in range(2)]
+            chunks = [(z0, min(Z, z0 + step)) for z0 in range(0, Z, step)]
+            evs = []
+            with torch.cuda.device(t.device):
+                self.stream.wait_event(self.ready)
+
+                def issue(i):
+                    z0, z1 = chunks[i]
+                    b = bufs[i & 1][:(z1 - z0) * Y * w]
+                    _engine._lib.check(lib.fdn_copy2d_async(
+                        b.data_ptr(), 4 * w, t.data_ptr() + 4 * (z0 * Y * X + x0), 4 * X, 4 * w, (z1 - z0) * Y, 1,
+                        self.stream.cuda_stream))
+                    e = torch.cuda.Event()
+                    e.record(self.stream)
+                    evs.append((e, b))
+                issue(0)
+                for i, (z0, z1) in enumerate(chunks):
+                    e, b = evs[i]
+                    e.synchronize()
+                    if i + 1 < len(chunks):
+                        issue(i + 1)
+                    np.copyto(dst[z0:z1, :, x0:x1], b.numpy().reshape(z1 - z0, Y, w), casting="unsafe")
+        except BaseException as e:
+            self.error = e
+
+    def wait(self):
+        if self.thread is not None:
+            self.thread.join()
+        self.stream.synchronize()
+        if self.error is not None:
+            raise self.error
+
+
 def warp_slice(reference, flow):
     '''src/flowdenoising.py:55-63 -- bilinear remap, replicate border, OpenCV's 1/32-px map quantiser.'''
     eng = _get_engine()
@@ -431,6 +601,9 @@ class GaussianDenoising():
             self._progress_done = base + Z + Y + X
             return self.filtered_vol
         flow = self._flow()
+        plan = self._overlap_plan(torch, ks)
+        if plan is not None:
+            return self._filter_overlapped(eng, ks, flow, *plan)
         d_in = _upload_volume(self.vol, torch, eng.device)
         a = torch.empty_like(d_in)
         b = torch.empty_like(d_in)
@@ -449,6 +622,84 @@ class GaussianDenoising():
             out = eng.transpose_yx(ot, a.view(Z, Y, X))
         dl = _Download(out, self.filtered_vol, torch)
         dl.wait()
+        dl_zy.wait()
+        self._end_device_call(Z + Y + X)
+        return self.filtered_vol
+
+    def _overlap_plan(self, torch, ks):
+        """(head, tail): output slices of the Z pass that run before the whole volume is on the device and columns
+        of the X pass whose download stays exposed; None = the plain sequence upload, passes, download."""
+        Z, Y, X = (int(v) for v in self.vol.shape)
+        if self._flow() is None or 4 * Z * Y * X < _OVERLAP_MIN_BYTES:
+            return None     # no-OF passes take a few milliseconds: nothing to hide a transfer behind
+        if 4 * Y * X > _STAGE_BYTES or 4 * Z * Y > _STAGE_BYTES:
+            return None     # a plane larger than a staging buffer
+        # pageable / non-float32 arrays move at the speed of a host copy: larger pieces keep the transfers hidden
+        head = min(64, Z // 2) if _is_pinned_f32(self.vol, torch) else Z // 4
+        tail = min(128, X // 2) if _is_pinned_f32(self.filtered_vol, torch) else X // 4
+        if head < 1 or tail < 1:
+            return None
+        return head, tail
+
+    def _filter_overlapped(self, eng, ks, flow, head, tail):
+        '''filter() for an in-core volume with the transfers hidden: the Z pass starts on its first `head` slices as
+        soon as they and their periodic neighbours are on the device, the last `tail` columns of the X pass run
+        while the other columns already travel home. Every slice still sees the same inputs: same bits.'''
+        torch = eng.torch
+        View = _engine.View
+        Z, Y, X = (int(v) for v in self.vol.shape)
+        rz = ks[0].size // 2
+        if head + 2 * rz >= Z:
+            ranges, head_key = [(0, Z)], 0
+        else:   # what the head needs first: its periodic neighbours at the far end, then slices 0 .. head + r
+            ranges, head_key = [(Z - rz, Z), (0, head + rz), (head + rz, Z - rz)], 1
+        up = _Upload(self.vol, torch, eng.device, ranges)
+        d_in = up.d
+        a = torch.empty_like(d_in)
+        b = torch.empty_like(d_in)
+        ot = torch.empty((Z, X, Y), dtype=torch.float32, device=d_in.device)
+        # one workspace for all three passes, sized after every volume-sized buffer exists
+        for v, k in ((View(Z, Z, 0, 1, Y, X, Y * X, X, Y * X, X), ks[0]),
+                     (View(Y, Y, 0, 1, Z, X, X, Y * X, X, Y * X), ks[1]),
+                     (View(X, X, 0, 1, Z, Y, Y, X * Y, Y, X * Y), ks[2])):
+            eng.reserve_workspace(v, k.size, flow)
+        # a pageable result array is usually untouched memory: map its pages while the passes run
+        pre = None if _is_pinned_f32(self.filtered_vol, torch) else _prefault(self.filtered_vol)
+        self._begin_device_call()
+        _mark(torch, "start")
+        try:
+            up.ready(head_key)
+            _mark(torch, "head uploaded")
+            eng.filter_view(d_in, a, View(Z, head, 0, 1, Y, X, Y * X, X, Y * X, X), ks[0], flow, exact=self.exact)
+            _mark(torch, "Z head")
+            up.ready(len(ranges) - 1)
+            _mark(torch, "all uploaded")
+            eng.filter_view(d_in, a[head:], View(Z, Z - head, head, 1, Y, X, Y * X, X, Y * X, X), ks[0], flow,
+                            exact=self.exact)
+        finally:
+            up.close()
+        _mark(torch, "Z tail")
+        eng.filter_along_axis(a, b, 1, ks[1], flow, exact=self.exact)          # b = Z+Y
+        _mark(torch, "Y")
+        dl_zy = _Download(b, self.vol, torch)                                   # ... goes home while X runs
+        vt = eng.transpose_yx(b, a.view(Z, X, Y))
+        out = d_in                                                              # dead since the Z pass
+        Xb = X - tail
+        eng.filter_view(vt, ot, View(X, Xb, 0, 1, Z, Y, Y, X * Y, Y, X * Y), ks[2], flow, exact=self.exact)
+        eng.transpose_strided(ot, 0, X * Y, Y, out, 0, Y * X, X, Z, Xb, Y)
+        _mark(torch, "X body")
+        if pre is not None:
+            pre.join()
+        dl_body = _DownloadCols(out, self.filtered_vol, 0, Xb, torch)
+        eng.filter_view(vt, ot.view(-1)[Xb * Y:], View(X, tail, Xb, 1, Z, Y, Y, X * Y, Y, X * Y), ks[2], flow,
+                        exact=self.exact)
+        eng.transpose_strided(ot, Xb * Y, X * Y, Y, out, Xb, Y * X, X, Z, tail, Y)
+        _mark(torch, "X tail")
+        dl_tail = _DownloadCols(out, self.filtered_vol, Xb, X, torch)
+        dl_body.wait()
+        _mark(torch, "body home")
+        dl_tail.wait()
+        _mark(torch, "tail home")
         dl_zy.wait()
         self._end_device_call(Z + Y + X)
         return self.filtered_vol

@@ -57,9 +57,11 @@ typedef struct fdn_of_params {
 
 /* Geometry of one volume view of a pass. The view holds n_in slices of (H, W). Output slice s (0..n_out-1)
  * is centred on input slice s+halo; its neighbours are input slices s+halo+d, d in [-r, r]. If periodic != 0
- * the neighbour index wraps modulo n_in (single-GPU / whole axis resident: halo = 0, n_out = n_in) exactly like
- * `% self.vol.shape[0]` in src/flowdenoising.py:312; otherwise the caller guarantees halo >= r slices on both
- * sides (multi-GPU slabs carry the periodic halo explicitly). */
+ * every input index wraps modulo n_in exactly like `% self.vol.shape[0]` in src/flowdenoising.py:312 (whole axis
+ * resident: halo = 0, n_out = n_in; a WINDOW of the axis: halo = first output slice, n_out <= n_in, d_out pointing at
+ * that slice -- the plugin runs the first / last slices of a pass as their own call so that the upload / download
+ * of the rest overlaps them); otherwise the caller guarantees halo >= r slices on both sides (multi-GPU slabs carry
+ * the periodic halo explicitly). */
 typedef struct fdn_view {
     int n_in, n_out, halo, periodic;
     int H, W;
@@ -136,6 +138,13 @@ int fdn_transpose_strided(const float* d_in, int64_t in_sn, int64_t in_sa, float
                           int n, int A, int B, void* stream);
 int fdn_copy3d(const float* d_in, int64_t in_sa, int64_t in_sb, int b0, int b_wrap, int c0, int c_wrap, float* d_out,
                int64_t out_sa, int64_t out_sb, int A, int B, int C, void* stream);
+
+/* Pitched copy on a stream (cudaMemcpy2DAsync): `rows` rows of `width_bytes`, direction 0 = host to device, 1 = device
+ * to host, 2 = device to device. Plumbing of the plugin's staging: a range of columns of the result volume goes home
+ * while the rest of the X pass still runs (the reference's classes own HOST arrays, src/flowdenoising.py:122-127,
+ * :285-290). Host memory should be page-locked, otherwise the copy is staged by the driver. */
+int fdn_copy2d_async(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes, size_t rows,
+                     int direction, void* stream);
 
 /* ---- stage entry points (parity tests; all operate on a batch of `n` dense images) ---- */
 /* Stage 1: Gaussian pyramid level: GaussianBlur(full-res, ksz, sigma) then bilinear resize to (h, w).
