@@ -481,6 +481,7 @@ def main():
     # ---- identity of the result: SHA-256 over the per-Z-slice SHA-256 digests, in Z order (independent of N) ----
     zyx = res[1]
     digests = slab_digests(zyx)
+    own_digests = list(digests)
     if world > 1:
         gathered = [None] * world
         dist.all_gather_object(gathered, digests)
@@ -547,25 +548,46 @@ def main():
         del host, pristine, obj
         fd.release_device_memory()
     elif world > 1 and not args.skip_e2e:
-        # host slab -> device -> distributed filter -> host slab, per rank (pinned); max over ranks
+        # host slab -> distributed filter -> host slab, per rank (pinned); max over ranks. filter_host() hides the
+        # copies behind the passes (edge slices first, Z pass / X pass split into windows); should it fail on every
+        # rank, the plain sequence upload, filter(), download is measured instead and the line says so.
         host = torch.empty(d_slab.shape, dtype=torch.float32, pin_memory=True)
         host.copy_(d_slab)
         out_host = torch.empty(d_slab.shape, dtype=torch.float32, pin_memory=True)
+        api = "flowdenoising_b200.dist.DistributedDenoiser.filter_host (pinned host slabs in / out, transfers hidden)"
+
+        def e2e_once(hidden):
+            if hidden:
+                return dd.filter_host(host, out_host, kernels)
+            d_tmp = host.to(device, non_blocking=True)
+            _zy, zyx_ = dd.filter(d_tmp, kernels)
+            out_host.copy_(zyx_, non_blocking=True)
+            return zyx_
+        hidden = True
+        try:
+            r_ = e2e_once(True); del r_     # warm-up: workspace and pinned staging reach their final sizes
+        except Exception as ex:             # noqa: BLE001 -- reported in the line
+            hidden = False
+            api = f"DistributedDenoiser.filter on pinned host slabs (filter_host failed: {type(ex).__name__}: {ex})"
+        flag = torch.tensor([1 if hidden else 0], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        hidden = bool(flag.item())
         times = []
         for i in range(2):
             barrier()
             t0 = time.perf_counter()
-            d_tmp = host.to(device, non_blocking=True)
-            zy, zyx = dd.filter(d_tmp, kernels)
-            out_host.copy_(zyx, non_blocking=True)
+            r_ = e2e_once(hidden)
             barrier()
             times.append(time.perf_counter() - t0)
+            del r_
         tt = torch.tensor([times[-1]], dtype=torch.float64, device=device)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = float(tt.item())
+        same = torch.tensor([1 if slab_digests(out_host) == own_digests else 0], dtype=torch.int32, device=device)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
         e2e = {"value": nvox / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(nvox * 4),
-               "d2h_bytes_per_step": int(nvox * 4), "ms_per_step": e2e_s * 1e3, "steps": 1,
-               "api": "flowdenoising_b200.dist.DistributedDenoiser.filter on pinned host slabs"}
+               "d2h_bytes_per_step": int(nvox * 4), "ms_per_step": e2e_s * 1e3, "steps": 1, "api": api,
+               "result_equals_device_run": bool(same.item())}
 
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample; its output slices are the parity reference ----
     cpu = None

@@ -178,6 +178,12 @@ class DeviceEngine:
                                            int(c0), int(cw), dst.data_ptr() + 4 * int(dst_off), int(out_sa),
                                            int(out_sb), int(A), int(B), int(C), _stream_ptr(torch)))
 
+    def copy2d_async(self, dst_ptr, dst_pitch, src_ptr, src_pitch, width_bytes, rows, direction, stream):
+        """fdn_copy2d_async on a torch stream: direction 0 = host to device, 1 = device to host, 2 = on the device."""
+        with self.torch.cuda.device(self.device):
+            _lib.check(self.lib.fdn_copy2d_async(int(dst_ptr), int(dst_pitch), int(src_ptr), int(src_pitch),
+                                                 int(width_bytes), int(rows), int(direction), stream.cuda_stream))
+
     def transpose_strided(self, src, src_off, in_sn, in_sa, dst, dst_off, out_sn, out_sb, n, A, B):
         """dst[i*out_sn + b*out_sb + a] = src[i*in_sn + a*in_sa + b] -- the transposing unpack of the re-slab."""
         torch = self.torch

@@ -4,7 +4,8 @@ packing / transposing unpack) exercised on CPU with the gloo backend, world size
 The compute object is a CPU stand-in built on the ORACLE (test infrastructure): it implements the four device
 operations DistributedDenoiser calls (filter_view, copy3d, transpose_strided, empty) with NumPy semantics identical
 to the C-ABI contracts in include/fdn_b200.h. The distributed result must equal the single-process oracle bit for
-bit, for both the no-OF and the OF path. The GPU twin of this test is tests/test_gpu_dist.py.
+bit, for both the no-OF and the OF path, through filter() (device slabs) and filter_host() (host slabs, passes split
+into windows). The GPU twin of this test is tests/test_gpu_dist.py.
 """
 import os
 import socket
@@ -80,6 +81,11 @@ def _worker(rank, world, port, shape, sigmas, use_of, result_dir):
         zy, zyx = dd.filter(torch.from_numpy(vol[zs:ze].copy()), kernels, want_zy=True)
         np.save(os.path.join(result_dir, f"zy_{rank}.npy"), zy.numpy())
         np.save(os.path.join(result_dir, f"zyx_{rank}.npy"), zyx.numpy())
+        # host slabs in / out with the Z pass and the X pass split into windows (the transfer-hiding sequence)
+        out_host = torch.full((ze - zs,) + tuple(shape[1:]), float("nan"), dtype=torch.float32)
+        res = dd.filter_host(torch.from_numpy(vol[zs:ze].copy()), out_host, kernels)
+        assert torch.equal(res, out_host)
+        np.save(os.path.join(result_dir, f"zyxh_{rank}.npy"), out_host.numpy())
     finally:
         dist.destroy_process_group()
 
@@ -88,6 +94,9 @@ def _worker(rank, world, port, shape, sigmas, use_of, result_dir):
     (2, (10, 12, 14), (1.0, 0.5, 1.0), False),      # r = 4 > slab/2: halo comes from both neighbours
     (3, (11, 13, 10), (0.5, 1.0, 0.5), False),      # uneven splits, X smaller than 2r+... wraps
     (2, (6, 40, 48), (0.5, 0.5, 0.5), True),        # OF path (r = 2), level 0 only for the thin passes
+    (2, (24, 12, 14), (0.5, 0.5, 0.5), False),      # filter_host splits the Z pass (head 3 of 12) and the X pass (6 + 1)
+    (3, (20, 13, 11), (0.5, 1.0, 0.5), False),      # ... with uneven slabs: Zl = 7, 7, 6 and Xl = 4, 4, 3 (tail 1)
+    (2, (16, 40, 48), (0.5, 0.5, 0.5), True),       # ... on the OF path
 ])
 def test_distributed_equals_single_process_oracle(tmp_path, world, shape, sigmas, use_of):
     port = _free_port()
@@ -102,6 +111,8 @@ def test_distributed_equals_single_process_oracle(tmp_path, world, shape, sigmas
     assert zy.shape == ref_zy.shape and not np.isnan(zy).any() and not np.isnan(zyx).any()
     assert np.array_equal(zy, ref_zy)
     assert np.array_equal(zyx, ref_zyx)
+    zyxh = np.concatenate([np.load(tmp_path / f"zyxh_{r}.npy") for r in range(world)])
+    assert np.array_equal(zyxh, ref_zyx)
 
 
 def test_split_range_covers_axis():

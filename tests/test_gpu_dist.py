@@ -41,6 +41,14 @@ def _worker(rank, world, port, shape, sigmas, use_of, out_dir):
         torch.cuda.synchronize()
         np.save(os.path.join(out_dir, f"zy_{rank}.npy"), zy.cpu().numpy())
         np.save(os.path.join(out_dir, f"zyx_{rank}.npy"), zyx.cpu().numpy())
+        # host slabs in / out: copy stream, the Z pass and the X pass split into windows, pitched downloads
+        host = torch.from_numpy(vol[zs:ze].copy()).pin_memory()
+        out_host = torch.full(host.shape, float("nan"), dtype=torch.float32).pin_memory()
+        for _ in range(2):      # the second call re-uses cached buffers while copies of the first may still be queued
+            res = dd.filter_host(host, out_host, kernels)
+        torch.cuda.synchronize()
+        assert torch.equal(res.cpu(), out_host)
+        np.save(os.path.join(out_dir, f"zyxh_{rank}.npy"), out_host.numpy())
     finally:
         dist.destroy_process_group()
 
@@ -66,3 +74,5 @@ def test_distributed_equals_single_gpu(tmp_path, world, shape, sigmas, use_of):
     zyx = np.concatenate([np.load(tmp_path / f"zyx_{r}.npy") for r in range(world)])
     assert np.array_equal(zy, ref_zy)
     assert np.array_equal(zyx, ref_zyx)
+    zyxh = np.concatenate([np.load(tmp_path / f"zyxh_{r}.npy") for r in range(world)])
+    assert np.array_equal(zyxh, ref_zyx)
