@@ -635,7 +635,8 @@ class GaussianDenoising():
         if 4 * Y * X > _STAGE_BYTES or 4 * Z * Y > _STAGE_BYTES:
             return None     # a plane larger than a staging buffer
         # pageable / non-float32 arrays move at the speed of a host copy: larger pieces keep the transfers hidden
-        head = min(64, Z // 2) if _is_pinned_f32(self.vol, torch) else Z // 4
+        # (pinned: about 256 MB of slices, 8 .. 64 of them -- the head's upload is the part that stays exposed)
+        head = min(Z // 2, max(8, min(64, (256 << 20) // (4 * Y * X)))) if _is_pinned_f32(self.vol, torch) else Z // 4
         tail = min(128, X // 2) if _is_pinned_f32(self.filtered_vol, torch) else X // 4
         if head < 1 or tail < 1:
             return None

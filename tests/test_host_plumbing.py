@@ -27,10 +27,12 @@ def test_overlap_plan_decisions(monkeypatch):
     assert _Obj((64, 256, 256))._overlap_plan(torch, ks) is None
     assert _Obj((512, 1024, 1024), of=False)._overlap_plan(torch, ks) is None
     assert _Obj((8, 4100, 4100))._overlap_plan(torch, ks) is None
-    # page-locked float32 arrays move at PCIe speed: 64 slices / 128 columns are enough
+    # page-locked float32 arrays move at PCIe speed: about 256 MB of slices / 128 columns are enough
     monkeypatch.setattr(fd, "_is_pinned_f32", lambda a, t: True)
     assert _Obj((512, 1024, 1024))._overlap_plan(torch, ks) == (64, 128)
-    assert _Obj((40, 2048, 2048))._overlap_plan(torch, ks) == (20, 128)
+    assert _Obj((256, 2048, 2048))._overlap_plan(torch, ks) == (16, 128)      # 16 MB slices: 256 MB of them
+    assert _Obj((40, 4000, 4000))._overlap_plan(torch, ks) == (8, 128)         # never fewer than 8 ...
+    assert _Obj((12, 4000, 4000))._overlap_plan(torch, ks) == (6, 128)         # ... or more than half the axis
     monkeypatch.setattr(fd, "_OVERLAP_MIN_BYTES", 0)
     assert _Obj((1, 64, 64))._overlap_plan(torch, ks) is None          # nothing to split
     assert _Obj((2, 64, 2))._overlap_plan(torch, ks) == (1, 1)
