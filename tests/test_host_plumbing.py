@@ -52,3 +52,21 @@ def test_prefault_leaves_the_values_alone(dtype):
     assert fd._prefault(a[:, :, ::2]) is None          # not contiguous: left alone
     ro = a.copy(); ro.setflags(write=False)
     assert fd._prefault(ro) is None
+
+
+@pytest.mark.parametrize("shape,src_t,dst_t", [((16, 512, 1024), np.float32, np.float32), ((16, 512, 1024), np.uint8, np.float32),
+                                               ((9, 700, 900), np.float32, np.uint8), ((1, 4096, 1024), np.float32, np.float32),
+                                               ((3, 7, 5), np.float32, np.int16)])
+def test_threaded_staging_copy_equals_copyto(shape, src_t, dst_t):
+    """_pcopy = np.copyto(..., casting="unsafe"), whatever the split over the host threads (pieces along axis 0)."""
+    rng = np.random.default_rng(5)
+    src = (rng.random(shape) * 250).astype(src_t)
+    got = np.zeros(shape, dst_t)
+    ref = np.zeros(shape, dst_t)
+    fd._pcopy(got, src)
+    np.copyto(ref, src, casting="unsafe")
+    assert got.tobytes() == ref.tobytes()
+    # a range of columns of a larger array (the column downloads), neighbours untouched
+    big = np.full(shape[:2] + (shape[2] + 9,), 7, dst_t)
+    fd._pcopy(big[:, :, 4:4 + shape[2]], src)
+    assert np.array_equal(big[:, :, 4:4 + shape[2]], ref) and (big[:, :, :4] == 7).all() and (big[:, :, -5:] == 7).all()
