@@ -93,15 +93,19 @@ class DeviceEngine:
     def _pick_chunk(self, view: View, klen: int, ofp: OfParams) -> int:
         """Largest chunk of output slices whose workspace fits the limit (default: 85 % of free HBM)."""
         torch = self.torch
-        limit = self.workspace_limit_bytes
-        if limit is None:
-            free, _total = torch.cuda.mem_get_info(self.device)
-            have = self._ws.numel() if self._ws is not None else 0
-            limit = int((free + have) * 0.85)
         need = lambda c: self.lib.fdn_workspace_bytes(C.byref(view), klen, C.byref(ofp), c)
         full = need(view.n_out)
         if full == 0:
             _lib.check(1)
+        limit = self.workspace_limit_bytes
+        if limit is None:
+            have = self._ws.numel() if self._ws is not None else 0
+            if full <= have:
+                # the workspace this engine already holds is enough: no driver query (cudaMemGetInfo blocks for
+                # milliseconds while a large host <-> device copy is in flight, tools/host_stall_lab.py)
+                return view.n_out
+            free, _total = torch.cuda.mem_get_info(self.device)
+            limit = int((free + have) * 0.85)
         if full <= limit:
             return view.n_out
         lo, hi = 1, view.n_out

@@ -70,3 +70,145 @@ def test_threaded_staging_copy_equals_copyto(shape, src_t, dst_t):
     big = np.full(shape[:2] + (shape[2] + 9,), 7, dst_t)
     fd._pcopy(big[:, :, 4:4 + shape[2]], src)
     assert np.array_equal(big[:, :, 4:4 + shape[2]], ref) and (big[:, :, :4] == 7).all() and (big[:, :, -5:] == 7).all()
+
+
+def test_pick_chunk_asks_the_driver_only_when_the_held_workspace_is_too_small():
+    """DeviceEngine._pick_chunk: whole view when the workspace already held is large enough (no cudaMemGetInfo: it
+    blocks while a large copy is in flight), otherwise sized from the free memory, by bisection when that is short."""
+    from types import SimpleNamespace
+    from flowdenoising_b200.engine import DeviceEngine
+    from flowdenoising_b200._lib import View, OfParams
+    calls = []
+
+    def mem_get_info(_dev):
+        calls.append(1)
+        return free[0], 1 << 40
+    free = [10_000]
+    eng = object.__new__(DeviceEngine)
+    eng.torch = SimpleNamespace(cuda=SimpleNamespace(mem_get_info=mem_get_info))
+    eng.lib = SimpleNamespace(fdn_workspace_bytes=lambda v, klen, ofp, c: 100 * (c + 16))   # slices + 2r of cache
+    eng.device = None
+    eng.workspace_limit_bytes = None
+    eng._ws = SimpleNamespace(numel=lambda: 5_000)
+    v = View(64, 32, 0, 1, 8, 8, 64, 8, 64, 8)
+    ofp = OfParams(3, 5, 3, 5, 1.2, 1)
+    assert eng._pick_chunk(v, 17, ofp) == 32 and not calls             # 4800 bytes fit the 5000 held
+    eng._ws = SimpleNamespace(numel=lambda: 1_000)
+    assert eng._pick_chunk(v, 17, ofp) == 32 and len(calls) == 1       # 4800 <= 0.85 * (10000 + 1000)
+    free[0] = 3_000
+    assert eng._pick_chunk(v, 17, ofp) == 18 and len(calls) == 2       # 100 * (c + 16) <= 3400 -> c = 18
+    eng._ws = None
+    free[0] = 1_000
+    with pytest.raises(Exception):
+        eng._pick_chunk(v, 17, ofp)                                    # not even one slice
+    eng.workspace_limit_bytes = 2_000                                  # an explicit limit never asks the driver
+    n = len(calls)
+    assert eng._pick_chunk(v, 17, ofp) == 4 and len(calls) == n
+
+
+class _FakeCuda:
+    """Stream / event stand-ins: the host-side sequencing of _Upload on CPU tensors (copies are synchronous here)."""
+
+    class Event:
+        def __init__(self, enable_timing=False):
+            self.recorded = False
+
+        def record(self, stream=None):
+            self.recorded = True
+
+        def synchronize(self):
+            assert self.recorded
+
+    class Stream:
+        cuda_stream = 0
+
+        def __init__(self, device=None):
+            self.waited = []
+
+        def wait_stream(self, other):
+            self.waited.append(other)
+
+        def wait_event(self, e):
+            assert e.recorded, "the compute stream was told to wait for an event that was never recorded"
+
+        def synchronize(self):
+            pass
+
+    _current = Stream()
+
+    @classmethod
+    def current_stream(cls):
+        return cls._current
+
+    class _Ctx:
+        def __init__(self, *_a):
+            pass
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *exc):
+            return False
+    stream = _Ctx
+    device = _Ctx
+
+
+class _FakeTorch:
+    """torch with a stand-in `cuda` namespace (everything else is the real module)."""
+    cuda = _FakeCuda
+
+    def __getattr__(self, name):
+        return getattr(torch, name)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.uint8])
+def test_upload_pieces_arrive_in_order_and_only_after_start(monkeypatch, dtype):
+    """_Upload: nothing moves before start(); ready(k) returns once pieces 0..k are in place; the pieces of the
+    transfer-hiding order {far end, head, rest} together are the whole volume (cast to float32 on the way)."""
+    ft = _FakeTorch()
+    monkeypatch.setattr(fd, "_pinned_pair", lambda t: [torch.empty(fd._STAGE_BYTES // 4, dtype=torch.float32)
+                                                       for _ in range(2)])
+    rng = np.random.default_rng(2)
+    Z, Y, X = 40, 64, 96
+    vol = (rng.random((Z, Y, X)) * 255).astype(dtype)
+    r, head = 4, 10
+    ranges = [(Z - r, Z), (0, head + r), (head + r, Z - r)]
+    up = fd._Upload(vol, ft, "cpu", ranges)
+    up.d.fill_(-1.0)
+    assert up.thread is None and not any(f.is_set() for f in up.flags)
+    assert float(up.d.max()) == -1.0                                   # allocated, not started
+    up.start()
+    up.ready(1)                                                         # far end + head
+    got = up.d.numpy()
+    assert np.array_equal(got[Z - r:], vol[Z - r:].astype(np.float32))
+    assert np.array_equal(got[:head + r], vol[:head + r].astype(np.float32))
+    up.ready(2)
+    up.close()
+    assert np.array_equal(up.d.numpy(), vol.astype(np.float32))
+    # a failing source surfaces on the calling thread instead of hanging ready()
+    class Bad:
+        shape = (Z, Y, X)
+
+        def __getitem__(self, k):
+            raise IOError("unreadable")
+    up2 = fd._Upload(Bad(), ft, "cpu", [(0, Z)])
+    up2.start()
+    with pytest.raises(IOError):
+        up2.ready(0)
+
+
+def test_upload_of_a_pinned_array_is_issued_by_start(monkeypatch):
+    """The direct (page-locked float32) route of _Upload: same contract, no host thread."""
+    ft = _FakeTorch()
+    monkeypatch.setattr(fd, "_is_pinned_f32", lambda a, t: True)
+    Z, Y, X = 12, 8, 16
+    vol = np.random.default_rng(4).random((Z, Y, X)).astype(np.float32)
+    up = fd._Upload(vol, ft, "cpu", [(10, 12), (0, 5), (5, 10)])
+    up.d.fill_(-1.0)
+    assert not any(e.recorded for e in up.events)
+    up.start()
+    assert up.thread is None and all(e.recorded for e in up.events) and all(f.is_set() for f in up.flags)
+    assert up.stream.waited == [ft.cuda.current_stream()]              # ordered after earlier users of the memory
+    up.ready(2)
+    up.close()
+    assert np.array_equal(up.d.numpy(), vol)
