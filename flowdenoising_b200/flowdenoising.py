@@ -227,12 +227,14 @@ class _Upload:
         self.flags = [threading.Event() for _ in self.ranges]
         self.error = None
         self.thread = None
+        self.started = False
 
     def start(self):
         """Issues the copies. Called after the caller's other allocations and workspace sizing: cudaMemGetInfo
         blocks for milliseconds while a large copy is in flight (tools/host_stall_lab.py), which would hold back
         the launches the copy is supposed to hide behind."""
         torch, vol = self.torch, self.vol
+        self.started = True
         self.stream.wait_stream(torch.cuda.current_stream())   # earlier users of this memory are done first
         if _is_pinned_f32(vol, torch):
             src = torch.from_numpy(vol)
@@ -278,6 +280,8 @@ class _Upload:
                 f.set()
 
     def ready(self, k):
+        if not self.started:
+            raise RuntimeError("_Upload.ready() before start()")
         self.flags[k].wait()
         if self.error is not None:
             raise self.error
