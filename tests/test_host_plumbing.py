@@ -212,3 +212,100 @@ def test_upload_of_a_pinned_array_is_issued_by_start(monkeypatch):
     up.ready(2)
     up.close()
     assert np.array_equal(up.d.numpy(), vol)
+
+
+# ---- filter() with hidden transfers, host logic only: an oracle-backed stand-in for the device engine (same method
+# contracts as DeviceEngine, CPU tensors, include/fdn_b200.h view semantics incl. windows of a periodic view) ----
+class _CpuEngine:
+    def __init__(self):
+        self.torch = _FakeTorch()
+        self.device = torch.device("cpu")
+        self.views = []
+
+    @staticmethod
+    def _flat(t):
+        assert t.is_contiguous()
+        return t.view(-1).numpy()
+
+    def reserve_workspace(self, view, klen, flow):
+        pass
+
+    def filter_view(self, d_in, d_out, v, kernel, flow, chunk=None, exact=True):
+        from oracle import fd_oracle as O
+        self.views.append((v.n_in, v.n_out, v.halo, v.periodic))
+        src = np.lib.stride_tricks.as_strided(self._flat(d_in), (v.n_in, v.H, v.W),
+                                              (4 * v.in_slice_stride, 4 * v.in_row_stride, 4))
+        dst = np.lib.stride_tricks.as_strided(self._flat(d_out), (v.n_out, v.H, v.W),
+                                              (4 * v.out_slice_stride, 4 * v.out_row_stride, 4))
+        assert v.periodic and 0 <= v.halo < v.n_in and v.n_out <= v.n_in
+        o = O.OracleDenoiser(1, np.ascontiguousarray(src), use_OF=flow is not None, backend="c",
+                             **({} if flow is None else dict(l=flow.levels, w=flow.winsize)))
+        for s in range(v.n_out):
+            idx = (s + v.halo) % v.n_in
+            o.filter_slice(0, idx, kernel)          # the oracle wraps like the reference (% shape)
+            dst[s] = o.filtered_vol[idx]
+
+    def filter_along_axis(self, vol, out, axis, kernel, flow, chunk=None, exact=True, scratch=None):
+        from flowdenoising_b200._lib import View
+        Z, Y, X = vol.shape
+        assert axis == 1
+        self.filter_view(vol, out, View(Y, Y, 0, 1, Z, X, X, Y * X, X, Y * X), kernel, flow)
+
+    def transpose_yx(self, src, dst=None):
+        n, A, B = src.shape
+        if dst is None:
+            dst = torch.empty((n, B, A), dtype=torch.float32)
+        dst.copy_(src.transpose(1, 2))
+        return dst
+
+    def transpose_strided(self, src, src_off, in_sn, in_sa, dst, dst_off, out_sn, out_sb, n, A, B):
+        s, d = self._flat(src), self._flat(dst)
+        i = np.arange(n)[:, None, None]
+        a = np.arange(A)[None, :, None]
+        b = np.arange(B)[None, None, :]
+        d[dst_off + i * out_sn + b * out_sb + a] = s[src_off + i * in_sn + a * in_sa + b]
+
+
+class _CpuDownload:
+    """Stand-in for _Download / _DownloadCols (device -> caller's array): inline copies."""
+
+    def __init__(self, t, dst, *cols_and_torch):
+        if len(cols_and_torch) == 3:
+            x0, x1, _t = cols_and_torch
+            np.copyto(dst[:, :, x0:x1], t.numpy()[:, :, x0:x1], casting="unsafe")
+        else:
+            np.copyto(dst, t.numpy(), casting="unsafe")
+
+    def wait(self):
+        pass
+
+
+@pytest.mark.parametrize("shape,head,tail,dtype", [((12, 24, 32), 3, 5, np.float32), ((12, 24, 32), 0, 7, np.float32),
+                                                   ((7, 24, 32), 3, 1, np.float32), ((12, 24, 32), 4, 8, np.uint8)])
+def test_filter_with_hidden_transfers_host_logic_vs_oracle(monkeypatch, shape, head, tail, dtype):
+    """_filter_overlapped on the stand-in engine == the oracle's filter(): order of the upload pieces, the windows of
+    the Z and the X pass (offsets into the output, wrap-around neighbours), the buffer roles (vol <- Z+Y,
+    filtered_vol <- Z+Y+X, src/flowdenoising.py:285-290), progress."""
+    from oracle import fd_oracle as O
+    monkeypatch.setattr(fd, "_pinned_pair", lambda t: [torch.empty(fd._STAGE_BYTES // 4, dtype=torch.float32)
+                                                       for _ in range(2)])
+    monkeypatch.setattr(fd, "_Download", _CpuDownload)
+    monkeypatch.setattr(fd, "_DownloadCols", _CpuDownload)
+    monkeypatch.setattr(fd.GaussianDenoising, "_begin_device_call", lambda self: None)
+    monkeypatch.setattr(fd.GaussianDenoising, "_end_device_call",
+                        lambda self, n: setattr(self, "_progress_done", self._progress_done + n))
+    base = O.synthetic_volume(shape, seed=9, noise_sigma=6.0)
+    vol = np.clip(base, 0, 255).astype(dtype)
+    kernels = [O.get_gaussian_kernel(0.5), O.get_gaussian_kernel(0.5), O.get_gaussian_kernel(0.75)]   # r = 2, 2, 3
+    ref = O.OracleDenoiser(1, vol.astype(np.float32), use_OF=True, l=2, w=5, backend="c")
+    ref_zyx = ref.filter(kernels)
+    obj = fd.FlowDenoising(1, vol.copy(), 2, 5)
+    eng = _CpuEngine()
+    res = obj._filter_overlapped(eng, [np.asarray(k, np.float64) for k in kernels], obj._flow(), head, tail)
+    Z, Y, X = shape
+    assert res is obj.filtered_vol and obj.progress == Z + Y + X
+    assert np.array_equal(res, ref_zyx.astype(dtype)) and np.array_equal(obj.vol, ref.vol.astype(dtype))
+    split_z = head > 0 and head + 4 < Z
+    want = ([(Z, head, 0, 1), (Z, Z - head, head, 1)] if split_z else [(Z, Z, 0, 1)]) + \
+           [(Y, Y, 0, 1), (X, X - tail, 0, 1), (X, tail, X - tail, 1)]
+    assert eng.views == want
